@@ -1,0 +1,108 @@
+"""CPU: host-side logic of the drop-in boundary (state_dict layout, feature resize, vocabulary,
+sharding + the world_size-2 gloo gather)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import video_captioning_b200 as vc
+from oracle import synth
+from oracle.caption_oracle import decode_caption as oracle_decode
+from oracle.caption_oracle import resize_features as oracle_resize
+from video_captioning_b200.predictor import resize_features
+from video_captioning_b200.sharding import gather_captions, shard_bounds
+
+
+@pytest.mark.parametrize("att", synth.ATTENTION_TYPES)
+def test_state_dict_layout_matches_reference_keys(att):
+    cfg = synth.make_config("tiny")
+    sd = synth.make_state_dict(cfg, 1000, att)
+    m = vc.VideoCaptioningModel(cfg, 1000, attention_type=att)
+    own = m.state_dict()
+    assert sorted(own) == sorted(sd)
+    for k in sd:
+        assert tuple(own[k].shape) == sd[k].shape, k
+
+
+def test_swapping_attention_module_like_the_oracle_does():
+    cfg = synth.make_config("tiny")
+    m = vc.VideoCaptioningModel(cfg, 1000)
+    m.decoder.attention = vc.LuongAttention(cfg, "dot")
+    assert m._desc()["attention"] == 1
+    m.decoder.attention = vc.MultiHeadAttention(cfg, 4)
+    assert m._desc()["attention"] == 4 and m._desc()["num_heads"] == 4
+    with pytest.raises(ValueError):
+        vc.create_attention_mechanism(cfg, "nope")
+
+
+def test_mismatched_hidden_dims_rejected():
+    cfg = synth.make_config("tiny")
+    cfg.model.decoder_hidden_dim = 64
+    with pytest.raises(ValueError, match="not supported"):
+        vc.VideoCaptioningModel(cfg, 1000)
+
+
+@pytest.mark.parametrize("tp", [5, 16, 17, 80, 200, 1000])
+def test_resize_features_matches_oracle(tp):
+    x = np.random.default_rng(tp).standard_normal((tp, 7)).astype(np.float32)
+    assert np.array_equal(resize_features(x, 16), oracle_resize(x, 16))
+    assert resize_features(x, 16).shape == (16, 7)
+
+
+def test_vocabulary_decode_matches_oracle():
+    v = vc.Vocabulary.from_words(["a", "man", "is", "running"])
+    assert len(v) == 8
+    for toks in ([1, 4, 5, 2, 6, 7, 0, 99], [4, 5, 6], [], [2, 4], [1, 1, 2]):
+        for rm in (True, False):
+            assert v.decode_caption(toks, rm) == oracle_decode(toks, v.idx2word, remove_special_tokens=rm)
+    v2 = vc.Vocabulary.from_package(v.to_package())
+    assert v2.word2idx == v.word2idx and v2.end_idx == 2
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 8, 65536, 1000):
+        for w in (1, 2, 4, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 3 if rank == 0 else 2
+    L = 4 + rank
+    toks = torch.full((n, L), 10 + rank, dtype=torch.int64)
+    lens = torch.full((n,), L, dtype=torch.int64)
+    t, l = gather_captions(toks, lens, pad_id=1)
+    q.put((rank, t.tolist(), l.tolist()))
+    dist.destroy_process_group()
+
+
+def test_gather_captions_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+    exp_t = [[10, 10, 10, 10, 1]] * 3 + [[11] * 5] * 2
+    for _, t, l in res:
+        assert t == exp_t and l == [4, 4, 4, 5, 5]

@@ -1,0 +1,312 @@
+"""ctypes binding of the C ABI in ``include/vc_b200.h`` (``libvc_b200.so``).
+
+There is deliberately no CPU or PyTorch fallback: if the library cannot be built/loaded, or a call
+returns a non-zero status, a ``RuntimeError`` is raised.  PyTorch is used here only for device memory
+(``torch.empty`` workspaces / outputs) and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+from typing import Dict, Optional
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_REPO_ROOT = os.path.dirname(_PKG_DIR)
+_CSRC = os.path.join(_PKG_DIR, "csrc")
+_INCLUDE = os.path.join(_REPO_ROOT, "include")
+LIB_PATH = os.path.join(_PKG_DIR, "libvc_b200.so")
+
+ATTN_BAHDANAU, ATTN_LUONG_DOT, ATTN_LUONG_GENERAL, ATTN_LUONG_CONCAT, ATTN_MULTIHEAD = range(5)
+PREC_FP32, PREC_BF16 = 0, 1
+METHOD_GREEDY, METHOD_BEAM = 0, 1
+
+ATTENTION_IDS = {
+    "bahdanau": ATTN_BAHDANAU, "luong_dot": ATTN_LUONG_DOT, "luong_general": ATTN_LUONG_GENERAL,
+    "luong_concat": ATTN_LUONG_CONCAT, "multihead": ATTN_MULTIHEAD,
+}
+PRECISION_IDS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+
+# every symbol include/vc_b200.h declares (tests check the .so exports all of them)
+EXPORTED_SYMBOLS = (
+    "vc_last_error", "vc_version", "vc_model_create", "vc_model_set_weight", "vc_model_finalize",
+    "vc_model_destroy", "vc_workspace_bytes", "vc_encoder_forward", "vc_attn_precompute",
+    "vc_decode_greedy", "vc_decode_beam", "vc_generate", "vc_forward_teacher", "vc_linear",
+    "vc_attention_step", "vc_beam_select",
+)
+
+
+class ModelDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "feature_dim", "hidden_dim", "embed_dim", "attn_dim", "vocab_size", "enc_layers", "dec_layers",
+        "attention", "num_heads", "precision")]
+
+
+class DecodeParams(ctypes.Structure):
+    _fields_ = [("method", ctypes.c_int32), ("beam_size", ctypes.c_int32), ("max_length", ctypes.c_int32),
+                ("start_token_id", ctypes.c_int32), ("end_token_id", ctypes.c_int32),
+                ("length_penalty", ctypes.c_float), ("temperature", ctypes.c_float),
+                ("diverse_beams", ctypes.c_int32)]
+
+
+def nvcc_command(out_path: str = LIB_PATH):
+    return ["nvcc", "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+            "-shared", "-Xcompiler", "-fPIC", "-I", _INCLUDE, "-o", out_path, os.path.join(_CSRC, "capi.cu")]
+
+
+def _sources_mtime() -> float:
+    files = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [os.path.join(_INCLUDE, "vc_b200.h")]
+    return max(os.path.getmtime(f) for f in files)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/capi.cu for sm_100a into libvc_b200.so (in-tree).  Cross-compiles without a GPU."""
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _sources_mtime():
+        return LIB_PATH
+    cmd = nvcc_command(LIB_PATH + ".tmp")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed building libvc_b200.so:\n" + proc.stdout + proc.stderr)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    if verbose:
+        print(proc.stdout + proc.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library() -> ctypes.CDLL:
+    """Load (building first if needed) the native library.  Raises if that is impossible."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            build_library()
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64, f32p, i32p = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p
+        sz = ctypes.c_size_t
+        lib.vc_last_error.restype = ctypes.c_char_p
+        lib.vc_last_error.argtypes = []
+        lib.vc_version.restype = ctypes.c_int
+        lib.vc_model_create.argtypes = [ctypes.POINTER(ModelDesc), ctypes.POINTER(vp)]
+        lib.vc_model_set_weight.argtypes = [vp, ctypes.c_char_p, f32p, i64, vp]
+        lib.vc_model_finalize.argtypes = [vp, vp]
+        lib.vc_model_destroy.argtypes = [vp]
+        lib.vc_model_destroy.restype = None
+        lib.vc_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
+        lib.vc_workspace_bytes.restype = sz
+        lib.vc_encoder_forward.argtypes = [vp, f32p, i32, i32, i32p, f32p, f32p, vp, sz, vp]
+        lib.vc_attn_precompute.argtypes = [vp, i32, i32, vp, sz, vp]
+        lib.vc_decode_greedy.argtypes = [vp, i32, i32, f32p, ctypes.POINTER(DecodeParams), i32p, f32p, vp, sz, vp]
+        lib.vc_decode_beam.argtypes = [vp, i32, i32, f32p, ctypes.POINTER(DecodeParams), i32p, i32p, f32p, vp, sz, vp]
+        lib.vc_generate.argtypes = [vp, f32p, i32, i32, i32p, f32p, ctypes.POINTER(DecodeParams), i32p, i32p, f32p,
+                                    f32p, vp, sz, vp]
+        lib.vc_forward_teacher.argtypes = [vp, f32p, i32, i32, i32p, f32p, i32p, i32, f32p, f32p, vp, sz, vp]
+        lib.vc_linear.argtypes = [i32, f32p, f32p, f32p, f32p, i32, i32, i32, i32, vp, sz, vp]
+        lib.vc_attention_step.argtypes = [vp, f32p, f32p, f32p, i32, i32, i32, f32p, f32p, vp, sz, vp]
+        lib.vc_beam_select.argtypes = [f32p, f32p, i32, i32, i32, i32p, i32p, f32p, vp, sz, vp]
+        for name in EXPORTED_SYMBOLS:
+            fn = getattr(lib, name)
+            if name not in ("vc_last_error", "vc_model_destroy", "vc_workspace_bytes"):
+                fn.restype = ctypes.c_int
+        _lib = lib
+        return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load_library().vc_last_error().decode(errors="replace")
+        if status == 1:
+            raise ValueError(f"{what}: {msg}")
+        raise RuntimeError(f"{what} failed (status {status}): {msg}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must live on a CUDA device: this package has no CPU path "
+                           f"(got device {t.device})")
+
+
+class NativeModel:
+    """Owns one ``vc_model_t`` handle built from a reference-layout state_dict."""
+
+    def __init__(self, desc: Dict[str, int], state_dict: Dict[str, torch.Tensor], device: torch.device):
+        self.lib = load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("NativeModel needs a CUDA device; there is no CPU fallback")
+        self.desc = ModelDesc(**desc)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.vc_model_create(ctypes.byref(self.desc), ctypes.byref(self._h)), "vc_model_create")
+            st = _stream(self.device)
+            keep = []
+            for key, val in state_dict.items():
+                t = val.detach().to(dtype=torch.float32).contiguous()
+                keep.append(t)
+                check(self.lib.vc_model_set_weight(self._h, key.encode(), _ptr(t), t.numel(), st),
+                      f"vc_model_set_weight({key})")
+            check(self.lib.vc_model_finalize(self._h, st), "vc_model_finalize")
+            torch.cuda.current_stream(self.device).synchronize()
+        self._ws: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                self.lib.vc_model_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+    # -- helpers
+    @property
+    def V(self):
+        return self.desc.vocab_size
+
+    @property
+    def H(self):
+        return self.desc.hidden_dim
+
+    def workspace_bytes(self, B, T, K, S) -> int:
+        return int(self.lib.vc_workspace_bytes(self._h, B, T, K, S))
+
+    def _workspace(self, B, T, K, S) -> torch.Tensor:
+        need = self.workspace_bytes(B, T, K, S)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _params(self, method, K, S, start, end, length_penalty=1.0, temperature=1.0, diverse=False):
+        return DecodeParams(METHOD_BEAM if method == "beam" else METHOD_GREEDY, int(K), int(S), int(start), int(end),
+                            float(length_penalty), float(temperature), int(bool(diverse)))
+
+    def _prep_feats(self, feats):
+        require_cuda(feats, "video_features")
+        f = feats.detach().to(dtype=torch.float32).contiguous()
+        if f.dim() != 3 or f.shape[2] != self.desc.feature_dim:
+            raise ValueError(f"video_features must be [B,T,{self.desc.feature_dim}], got {tuple(f.shape)}")
+        return f
+
+    @staticmethod
+    def _prep_mask(mask, B, T, device):
+        if mask is None:
+            return None, None
+        m = mask.detach().to(device=device, dtype=torch.float32).contiguous()
+        if tuple(m.shape) != (B, T):
+            raise ValueError(f"video_mask must be [{B},{T}], got {tuple(m.shape)}")
+        lengths = m.sum(dim=1).to(torch.int32).contiguous()   # encoder.py:75
+        return m, lengths
+
+    # -- entry points
+    def encoder_forward(self, feats, mask=None):
+        f = self._prep_feats(feats)
+        B, T, _ = f.shape
+        m, lengths = self._prep_mask(mask, B, T, self.device)
+        enc_out = torch.empty(B, T, self.H, dtype=torch.float32, device=self.device)
+        final = torch.empty(B, self.H, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            ws = self._workspace(B, T, 1, 1)
+            check(self.lib.vc_encoder_forward(self._h, _ptr(f), B, T, _ptr(lengths), _ptr(enc_out), _ptr(final),
+                                              _ptr(ws), ws.numel(), _stream(self.device)), "vc_encoder_forward")
+        return enc_out, final
+
+    def generate(self, feats, start, end, max_length, mask=None, method="greedy", beam_size=5, length_penalty=1.0,
+                 temperature=1.0, diverse=False, want_attention=True):
+        f = self._prep_feats(feats)
+        B, T, _ = f.shape
+        m, lengths = self._prep_mask(mask, B, T, self.device)
+        S = int(max_length)
+        beam = method == "beam"
+        K = int(beam_size) if beam else 1
+        p = self._params(method, K, S, start, end, length_penalty, temperature, diverse)
+        tokens = torch.empty(B, S + 1 if beam else S, dtype=torch.int32, device=self.device)
+        lens = torch.empty(B, dtype=torch.int32, device=self.device) if beam else None
+        scores = torch.empty(B, dtype=torch.float32, device=self.device) if beam else None
+        attn = torch.empty(B, S, T, dtype=torch.float32, device=self.device) if (want_attention and not beam) else None
+        with torch.cuda.device(self.device):
+            ws = self._workspace(B, T, K, S)
+            check(self.lib.vc_generate(self._h, _ptr(f), B, T, _ptr(lengths), _ptr(m), ctypes.byref(p), _ptr(tokens),
+                                       _ptr(lens), _ptr(scores), _ptr(attn), _ptr(ws), ws.numel(),
+                                       _stream(self.device)), "vc_generate")
+        return tokens, lens, scores, attn
+
+    def forward_teacher(self, feats, input_tokens, mask=None, want_attention=True):
+        f = self._prep_feats(feats)
+        B, T, _ = f.shape
+        m, lengths = self._prep_mask(mask, B, T, self.device)
+        tok = input_tokens.detach().to(device=self.device, dtype=torch.int32).contiguous()
+        L = tok.shape[1]
+        logits = torch.empty(B, L, self.V, dtype=torch.float32, device=self.device)
+        attn = torch.empty(B, L, T, dtype=torch.float32, device=self.device) if want_attention else None
+        with torch.cuda.device(self.device):
+            ws = self._workspace(B, T, 1, L)
+            check(self.lib.vc_forward_teacher(self._h, _ptr(f), B, T, _ptr(lengths), _ptr(m), _ptr(tok), L,
+                                              _ptr(logits), _ptr(attn), _ptr(ws), ws.numel(), _stream(self.device)),
+                  "vc_forward_teacher")
+        return logits, attn
+
+    def attention_step(self, enc_out, hidden, mask, K):
+        require_cuda(enc_out, "enc_out")
+        e = enc_out.detach().float().contiguous()
+        h = hidden.detach().float().contiguous()
+        B, T, H = e.shape
+        R = B * K
+        m = None if mask is None else mask.detach().float().contiguous()
+        ctx = torch.empty(R, H, dtype=torch.float32, device=self.device)
+        w = torch.empty(R, T, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            ws = self._workspace(B, T, K, 1)
+            check(self.lib.vc_attention_step(self._h, _ptr(e), _ptr(h), _ptr(m), B, T, K, _ptr(ctx), _ptr(w), _ptr(ws),
+                                             ws.numel(), _stream(self.device)), "vc_attention_step")
+        return ctx, w
+
+
+def linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, precision: str = "fp32",
+           apply_tanh: bool = False) -> torch.Tensor:
+    """``A @ W.T + bias`` through the native GEMM kernel of the given precision (parity-test entry)."""
+    require_cuda(A, "A")
+    lib = load_library()
+    A = A.detach().float().contiguous()
+    W = W.detach().float().contiguous()
+    b = None if bias is None else bias.detach().float().contiguous()
+    M, K = A.shape
+    N = W.shape[0]
+    C = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    ws = torch.empty(2 * (M * K + N * K) + 1024, dtype=torch.uint8, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib.vc_linear(PRECISION_IDS[precision], _ptr(A), _ptr(W), _ptr(b), _ptr(C), M, N, K, int(apply_tanh),
+                            _ptr(ws), ws.numel(), _stream(A.device)), "vc_linear")
+    return C
+
+
+def beam_select(logits: torch.Tensor, scores: torch.Tensor, B: int, K: int):
+    """One reference beam selection step (video_captioning_model.py:209-220) on the device."""
+    require_cuda(logits, "logits")
+    lib = load_library()
+    lg = logits.detach().float().contiguous()
+    sc = scores.detach().float().contiguous()
+    V = lg.shape[1]
+    R = B * K
+    parent = torch.empty(R, dtype=torch.int32, device=lg.device)
+    token = torch.empty(R, dtype=torch.int32, device=lg.device)
+    new_scores = torch.empty(R, dtype=torch.float32, device=lg.device)
+    ws = torch.empty(R * K * 8 + R * 32 + B * 32 + 8192, dtype=torch.uint8, device=lg.device)
+    with torch.cuda.device(lg.device):
+        check(lib.vc_beam_select(_ptr(lg), _ptr(sc), B, K, V, _ptr(parent), _ptr(token), _ptr(new_scores), _ptr(ws),
+                                 ws.numel(), _stream(lg.device)), "vc_beam_select")
+    return parent, token, new_scores

@@ -1,0 +1,110 @@
+// Common device/host helpers for the B200 caption-generation kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "vc_b200.h"
+
+namespace vc {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- error plumbing (no exceptions cross the C ABI)
+// Status codes are the public VC_* enum of include/vc_b200.h.
+void set_error(const char* fmt, ...);   // defined in capi.cu (thread-local message)
+
+#define VC_CUDA(expr)                                                                  \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      vc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return VC_ERR_CUDA;                                                          \
+    }                                                                                  \
+  } while (0)
+
+#define VC_CHECK(cond, ...)                                                            \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      vc::set_error(__VA_ARGS__);                                                      \
+      return VC_ERR_INVALID;                                                       \
+    }                                                                                  \
+  } while (0)
+
+#define VC_TRY(expr)                 \
+  do {                               \
+    int _s = (expr);                 \
+    if (_s != VC_OK) return _s;  \
+  } while (0)
+
+// ---------------------------------------------------------------- type helpers
+__device__ __forceinline__ float to_float(float x) { return x; }
+__device__ __forceinline__ float to_float(bf16 x) { return __bfloat162float(x); }
+template <class T> __device__ __forceinline__ T from_float(float x);
+template <> __device__ __forceinline__ float from_float<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 from_float<bf16>(float x) { return __float2bfloat16_rn(x); }
+
+// Load 4 consecutive elements as floats (pointer 16B- (float) / 8B- (bf16) aligned).
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+  v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+// 8 consecutive elements (32B float / 16B bf16 aligned)
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  uint4 t = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+
+// Precise and fast transcendental flavours.  PRECISE is used by the fp32 parity mode (bit-level
+// token parity against the CPU reference needs full-precision tanhf/expf).
+template <bool PRECISE> __device__ __forceinline__ float tanh_(float x) {
+  if (PRECISE) return tanhf(x);
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool PRECISE> __device__ __forceinline__ float sigmoid_(float x) {
+  if (PRECISE) return 1.0f / (1.0f + expf(-x));
+  // sigmoid(x) = 0.5*tanh(0.5x)+0.5 : one MUFU op
+  return fmaf(0.5f, tanh_<false>(0.5f * x), 0.5f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace vc

@@ -1,0 +1,168 @@
+"""VideoCaptioningModel: the reference's model API over the native B200 path.
+
+Same constructor, ``generate(...)`` signature, return dict and ``state_dict`` layout as the reference's
+``src/models/video_captioning_model.py`` (ctor :13-33, forward :35-77, generate :79-125), so a reference
+checkpoint loads with ``load_state_dict`` and ``predict.py``-style callers work unchanged.  All
+arithmetic runs in ``libvc_b200.so``; there is no PyTorch fallback.
+
+Semantics kept on purpose (SURVEY.md sections 3.3, 8a):
+  * greedy: tokens [B, L<=S] without START; stops only when every row emits END in the same step
+    (decoder.py:275); ``attention_weights`` [B, L, T].
+  * beam: the reference initialises all K beam scores to 0 (:194) so beams tie and the result equals
+    greedy with START prepended, truncated after the first END.  Its batched (B>1) bookkeeping is
+    broken (:277-282, RuntimeError on staggered END), and the Predictor only ever calls it with B=1
+    (predictor.py:102).  Batched contract here: row i == the reference's B=1 call on video i, rows
+    right-padded with START (:288-300).  ``diverse_beams=True`` opts into standard beam search.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _native
+from .decoder import CaptionDecoder
+from .encoder import VideoEncoder
+
+
+def _attention_desc(att) -> Dict[str, int]:
+    return {"attention": _native.ATTENTION_IDS[att.attention_kind], "num_heads": int(getattr(att, "num_heads", 1))}
+
+
+def standalone_attention_handle(att) -> "_native.NativeModel":
+    """Native handle for calling an attention module on its own (tests / explain): a minimal model
+    whose non-attention weights are zeros."""
+    p = next(att.parameters(), None)
+    device = p.device if p is not None else torch.device("cuda")
+    key = tuple((n, t._version, t.data_ptr()) for n, t in att.state_dict().items()) + (str(device),)
+    cached = getattr(att, "_standalone", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    H, A = att.encoder_dim, att.attention_dim
+    F = E = 64
+    V = 8
+    desc = dict(feature_dim=F, hidden_dim=H, embed_dim=E, attn_dim=A, vocab_size=V, enc_layers=1, dec_layers=1,
+                precision=_native.PREC_FP32, **_attention_desc(att))
+    z = lambda *s: torch.zeros(*s, device=device)
+    sd = {"encoder.feature_projection.weight": z(H, F), "encoder.feature_projection.bias": z(H),
+          "encoder.output_projection.weight": z(H, 2 * H), "encoder.output_projection.bias": z(H),
+          "decoder.embedding.weight": z(V, E), "decoder.lstm.weight_ih_l0": z(4 * H, E + H),
+          "decoder.lstm.weight_hh_l0": z(4 * H, H), "decoder.lstm.bias_ih_l0": z(4 * H), "decoder.lstm.bias_hh_l0": z(4 * H),
+          "decoder.context_projection.weight": z(H, 2 * H + E), "decoder.context_projection.bias": z(H),
+          "decoder.output_projection.weight": z(V, H), "decoder.output_projection.bias": z(V)}
+    for sfx in ("", "_reverse"):
+        sd[f"encoder.lstm.weight_ih_l0{sfx}"] = z(4 * H, H)
+        sd[f"encoder.lstm.weight_hh_l0{sfx}"] = z(4 * H, H)
+        sd[f"encoder.lstm.bias_ih_l0{sfx}"] = z(4 * H)
+        sd[f"encoder.lstm.bias_hh_l0{sfx}"] = z(4 * H)
+    for n, t in att.state_dict().items():
+        sd["decoder.attention." + n] = t
+    h = _native.NativeModel(desc, sd, device)
+    att._standalone = (key, h)
+    return h
+
+
+class VideoCaptioningModel(nn.Module):
+    """Encoder-decoder captioning model; parameters in the reference layout, compute in CUDA."""
+
+    def __init__(self, config, vocabulary_size: int, attention_type: str = "bahdanau", num_heads: int = 8,
+                 precision: str = "fp32", chunk_size: int = 2048):
+        super().__init__()
+        if precision not in _native.PRECISION_IDS:
+            raise ValueError(f"precision must be one of {list(_native.PRECISION_IDS)}")
+        self.config = config
+        self.vocabulary_size = vocabulary_size
+        self.encoder = VideoEncoder(config)
+        self.decoder = CaptionDecoder(config, vocabulary_size, attention_type, num_heads)
+        self.feature_extractor = None     # CNN extractors are out of scope (precomputed features)
+        self.precision = precision
+        self.chunk_size = int(chunk_size)  # videos per native call (bounds the workspace)
+        self._native_key = None
+        self._native_handle: Optional[_native.NativeModel] = None
+        self.encoder._owner = weakref.ref(self)
+
+    # ------------------------------------------------------------------ native handle management
+    def set_precision(self, precision: str) -> "VideoCaptioningModel":
+        if precision not in _native.PRECISION_IDS:
+            raise ValueError(f"precision must be one of {list(_native.PRECISION_IDS)}")
+        self.precision = precision
+        return self
+
+    def _desc(self) -> Dict[str, int]:
+        m = self.config.model
+        d = dict(feature_dim=m.cnn_feature_dim, hidden_dim=m.encoder_hidden_dim, embed_dim=m.embedding_dim,
+                 attn_dim=m.attention_dim, vocab_size=self.vocabulary_size, enc_layers=m.encoder_num_layers,
+                 dec_layers=m.decoder_num_layers, precision=_native.PRECISION_IDS[self.precision])
+        d.update(_attention_desc(self.decoder.attention))
+        return d
+
+    def _handle(self) -> _native.NativeModel:
+        """(Re)build the native handle when parameters, device, precision or attention module changed."""
+        sd = self.state_dict()
+        p = next(self.parameters())
+        if not p.is_cuda:
+            raise RuntimeError("VideoCaptioningModel must be moved to a CUDA device (model.to('cuda')); "
+                               "this package has no CPU path")
+        key = (self.precision, str(p.device), self.decoder.attention.attention_kind,
+               tuple((n, t._version, t.data_ptr()) for n, t in sd.items()))
+        if self._native_handle is None or key != self._native_key:
+            self._native_handle = None
+            self._native_handle = _native.NativeModel(self._desc(), sd, p.device)
+            self._native_key = key
+        return self._native_handle
+
+    # ------------------------------------------------------------------ reference API
+    def generate(self, video_features: torch.Tensor, start_token_id: int, end_token_id: int, max_length: int = 20,
+                 video_mask: Optional[torch.Tensor] = None, method: str = "greedy", **kwargs) -> Dict[str, torch.Tensor]:
+        """video_captioning_model.py:79-125.  kwargs: greedy ``temperature``; beam ``beam_size``,
+        ``length_penalty`` (+ opt-in ``diverse_beams``)."""
+        if method not in ("greedy", "beam"):
+            raise ValueError(f"Unsupported generation method: {method}")
+        if method == "greedy":
+            allowed = {"temperature"}
+        else:
+            allowed = {"beam_size", "length_penalty", "diverse_beams"}
+        bad = set(kwargs) - allowed
+        if bad:
+            raise TypeError(f"generate(method='{method}') got unexpected keyword arguments {sorted(bad)}")
+        h = self._handle()
+        B = video_features.shape[0]
+        outs = []
+        for lo in range(0, B, self.chunk_size):
+            hi = min(B, lo + self.chunk_size)
+            mk = None if video_mask is None else video_mask[lo:hi]
+            outs.append(h.generate(video_features[lo:hi], start_token_id, end_token_id, max_length, mk, method,
+                                   beam_size=kwargs.get("beam_size", 5), length_penalty=kwargs.get("length_penalty", 1.0),
+                                   temperature=kwargs.get("temperature", 1.0), diverse=kwargs.get("diverse_beams", False)))
+        tokens = torch.cat([o[0] for o in outs], dim=0)
+        if method == "greedy":
+            attn = torch.cat([o[3] for o in outs], dim=0)
+            # decoder.py:275: the loop stops after the first step at which every row emitted END
+            all_end = (tokens == end_token_id).all(dim=0)
+            idx = torch.nonzero(all_end)
+            L = int(idx[0, 0]) + 1 if idx.numel() else tokens.shape[1]
+            return {"generated_tokens": tokens[:, :L].to(torch.int64), "attention_weights": attn[:, :L]}
+        lens = torch.cat([o[1] for o in outs], dim=0)
+        scores = torch.cat([o[2] for o in outs], dim=0)
+        L = int(lens.max())
+        return {"generated_tokens": tokens[:, :L].to(torch.int64), "lengths": lens.to(torch.int64), "scores": scores}
+
+    def forward(self, video_features, input_tokens, target_tokens, video_mask=None) -> Dict[str, torch.Tensor]:
+        """Teacher-forced forward, video_captioning_model.py:35-77 (inference only: no autograd graph)."""
+        h = self._handle()
+        logits, attn = h.forward_teacher(video_features, input_tokens, video_mask)
+        enc_out, _ = h.encoder_forward(video_features, video_mask)
+        return {"logits": logits, "encoder_outputs": enc_out, "attention_weights": attn, "target_tokens": target_tokens}
+
+    def get_trainable_parameters(self) -> int:
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    def freeze_encoder(self) -> None:
+        for p in self.encoder.parameters():
+            p.requires_grad = False
+
+    def unfreeze_encoder(self) -> None:
+        for p in self.encoder.parameters():
+            p.requires_grad = True
