@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- captions/sec of the batched caption-generation path on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (CPU arm: the reference algorithm on host cores)
+
+A "step" = one pass of the whole hot path (bi-LSTM encoder -> hoisted attention projections -> S decode
+steps with beam search) over one batch of synthetic videos.  Default workload = BASELINE.json configs[1]:
+beam-5, 1024 MSVD-shape videos (80 x 4096 features, H=E=A=512, V=10k, max_len 20), Bahdanau, bf16.
+`value`  : captions/s with the features already resident in HBM (CUDA events, max over ranks).
+`e2e`    : captions/s through the public API VideoCaptioningModel.generate with HOST (pinned) features:
+           H2D copy of the features + generate + D2H of tokens/lengths inside the timed region.
+`roofline`: for the kernel class with the largest share of device time, measured with CUDA events on
+           the launching stream in an instrumented pass of the same workload (vc_profile_begin/end).
+`cpu_baseline`: the oracle port of the reference timed on the host cores on a bounded sample.
+Weights are random-init (oracle.synth, reference layout/initialiser distributions); data synthetic.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+START, END = 1, 2
+
+WORKLOADS = {
+    # name: shape, attention, method, K, S, per-GPU batch, precision
+    "c2_beam5_msvd_bf16": dict(shape="msvd", attention="bahdanau", method="beam", K=5, S=20, B=1024, precision="bf16"),
+    "c1_greedy_msvd_fp32": dict(shape="msvd", attention="bahdanau", method="greedy", K=1, S=20, B=32, precision="fp32"),
+    "c2_beam5_msvd_fp32": dict(shape="msvd", attention="bahdanau", method="beam", K=5, S=20, B=256, precision="fp32"),
+    "c3_luong_general_h1024": dict(shape="c3", attention="luong_general", method="beam", K=5, S=20, B=1024, precision="bf16"),
+    "c3_luong_dot_h1024": dict(shape="c3", attention="luong_dot", method="beam", K=5, S=20, B=1024, precision="bf16"),
+    "c4_multihead_resnet": dict(shape="c4", attention="multihead", method="beam", K=3, S=20, B=1024, precision="bf16"),
+    "c5_vocab30k_len30": dict(shape="c5", attention="bahdanau", method="beam", K=5, S=30, B=1024, precision="bf16"),
+}
+DEFAULT_WORKLOAD = "c2_beam5_msvd_bf16"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, source="fallback")
+
+
+# ---------------------------------------------------------------------------- algorithmic work per kernel class
+def class_work(wl, cfgm, B):
+    """Algorithmic FLOPs and HBM bytes per STEP (whole batch) for each kernel class.
+    bytes are the unavoidable traffic at the class's operand types (b = bytes/element of activations)."""
+    H, E, A, F, V, T = (cfgm.encoder_hidden_dim, cfgm.embedding_dim, cfgm.attention_dim, cfgm.cnn_feature_dim,
+                        cfgm.vocab_size, cfgm.video_sequence_length)
+    K, S = wl["K"], wl["S"]
+    Le, Ld = cfgm.encoder_num_layers, cfgm.decoder_num_layers
+    R = B * K
+    b = 2 if wl["precision"] == "bf16" else 4
+    att = wl["attention"]
+    w = {}
+    w["convert"] = dict(flops=0, bytes=B * T * F * (4 + 2))
+    w["enc_feature_proj"] = dict(flops=2 * B * T * F * H, bytes=B * T * F * b + H * F * b + B * T * H * b)
+    fl = by = 0
+    for l in range(Le):
+        inp = H if l == 0 else 2 * H
+        fl += 2 * B * T * inp * 8 * H
+        by += B * T * inp * b + 8 * H * inp * b + B * T * 8 * H * b
+    w["enc_input_proj"] = dict(flops=fl, bytes=by)
+    # per layer, per direction, per timestep: h[B,H] . W_hh[4H,H]^T, + xproj read, h write, c r/w
+    w["enc_recurrent"] = dict(flops=Le * 2 * T * 2 * B * H * 4 * H,
+                              bytes=Le * 2 * T * (B * H * b + 4 * H * H * b + B * 4 * H * b + B * H * b + 2 * B * H * 4))
+    w["enc_output_proj"] = dict(flops=2 * (B * T + B) * 2 * H * H, bytes=B * T * 2 * H * b + B * T * H * b)
+    if att in ("bahdanau", "luong_concat"):
+        w["attn_precompute"] = dict(flops=2 * B * T * H * A, bytes=B * T * H * b + B * T * A * b)
+        w["attn_query_proj"] = dict(flops=S * 2 * R * H * A, bytes=S * (R * H * b + A * H * b + R * A * 4))
+        # keys + enc_out read once per VIDEO-step, q read, ctx write
+        w["attn_step"] = dict(flops=S * R * (2 * T * A + 2 * T * H), tanh=S * R * T * A,
+                              bytes=S * (B * T * (A + H) * b + R * A * 4 + R * H * b))
+    elif att == "multihead":
+        w["attn_precompute"] = dict(flops=4 * B * T * H * H, bytes=B * T * H * b * 3)
+        w["attn_query_proj"] = dict(flops=S * 2 * R * H * H, bytes=S * (R * H * b + H * H * b + R * H * 4))
+        w["attn_step"] = dict(flops=S * R * 4 * T * H, bytes=S * (B * T * 2 * H * b + R * H * 4 + R * H * b))
+        w["attn_output_proj"] = dict(flops=S * 2 * R * H * H, bytes=S * (2 * R * H * b + H * H * b))
+    else:
+        w["attn_precompute"] = dict(flops=0, bytes=0)
+        if att == "luong_general":
+            w["attn_query_proj"] = dict(flops=S * 2 * R * H * H, bytes=S * (R * H * b + H * H * b + R * H * 4))
+        w["attn_step"] = dict(flops=S * R * 4 * T * H, bytes=S * (B * T * H * b + R * H * 4 + R * H * b))
+    fl = by = 0
+    for l in range(Ld):
+        kin = (E + H if l == 0 else H) + H
+        fl += 2 * R * kin * 4 * H
+        by += R * kin * b + 4 * H * kin * b + 2 * R * H * b + 2 * R * H * 4
+    w["dec_lstm"] = dict(flops=S * fl, bytes=S * by)
+    w["dec_context_proj"] = dict(flops=S * 2 * R * (2 * H + E) * H, bytes=S * (R * (2 * H + E) * b + (2 * H + E) * H * b + R * H * b))
+    # logits are materialised in fp32 by this version (written by the GEMM, read by select)
+    w["dec_vocab"] = dict(flops=S * 2 * R * H * V, bytes=S * (R * H * b + V * H * b + R * V * 4))
+    w["select"] = dict(flops=0, bytes=S * R * V * 4)
+    w["reorder_embed"] = dict(flops=0, bytes=(S - 1) * R * (Ld * (2 * H * b + 2 * H * 4) + 2 * E * b))
+    w["misc"] = dict(flops=0, bytes=0)
+    return w
+
+
+TENSOR_CLASSES = {"enc_feature_proj", "enc_input_proj", "enc_recurrent", "enc_output_proj", "attn_precompute",
+                  "attn_query_proj", "attn_output_proj", "dec_lstm", "dec_context_proj", "dec_vocab"}
+
+
+# ---------------------------------------------------------------------------- clocks sampling
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                smax = float(f[1])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[0]))
+                    for n, v in zip(names, f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(n)
+            except ValueError:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------- CPU arm (oracle port of the reference)
+def cpu_reference_run(wl, n_videos, threads=None):
+    """Times the reference algorithm (oracle port) on the host cores.  Beam is run the way the reference's
+    predict.py batch really runs it: one B=1 call per video (predictor.py:217,464; the batched call raises
+    on staggered END).  Returns (captions/s, seconds, threads)."""
+    from oracle import synth
+    from oracle.caption_oracle import CaptionOracle
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    cfg = synth.make_config(wl["shape"])
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, wl["attention"], seed=0)
+    feats = synth.make_features(n_videos, cfg.model.video_sequence_length, cfg.model.cnn_feature_dim, seed=1)
+    o = CaptionOracle(sd)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        if wl["method"] == "beam":
+            o.beam(feats, START, END, max_length=wl["S"], beam_size=wl["K"])
+        else:
+            o.greedy(feats, START, END, max_length=wl["S"])
+    dt = time.perf_counter() - t0
+    return n_videos / dt, dt, torch.get_num_threads()
+
+
+def run_reference_arm(args, wl, wl_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_videos
+    vals = []
+    for _ in range(args.warmup and 1):
+        cpu_reference_run(wl, max(2, n // 4))
+    for _ in range(max(1, min(args.steps, 3))):
+        v, dt, th = cpu_reference_run(wl, n)
+        vals.append((v, dt))
+    v = float(np.median([x[0] for x in vals]))
+    dt = float(np.median([x[1] for x in vals]))
+    line = {"impl": "reference", "metric": "captions/sec", "value": v, "unit": "captions/s", "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "sample_videos": n, **{k: wl[k] for k in ("method", "K", "S", "attention")}},
+            "cpu_baseline": {"value": v, "unit": "captions/s", "cores": th, "kind": "port",
+                             "sample": f"{n} videos per step, oracle port of the reference run per video (B=1) as predict.py batch does"},
+            "e2e": {"value": v, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="videos per GPU per step (default: workload's)")
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--cpu-videos", type=int, default=48, help="bounded CPU-baseline sample (videos)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-json", default=None, help="write the per-class device-time breakdown here")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["B"] = args.batch
+    if args.precision:
+        wl["precision"] = args.precision
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl, args.workload)
+        return
+
+    import torch.distributed as dist
+    import video_captioning_b200 as vc
+    from oracle import synth   # synthetic weights/features only (shared recipe); never on the timed path
+    from video_captioning_b200 import _native
+    from video_captioning_b200.sharding import gather_captions
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = synth.make_config(wl["shape"])
+    cm = cfg.model
+    V, T, F = cm.vocab_size, cm.video_sequence_length, cm.cnn_feature_dim
+    B, K, S = wl["B"], wl["K"], wl["S"]
+    sd = synth.make_state_dict(cfg, V, wl["attention"], seed=0)
+    model = vc.VideoCaptioningModel(cfg, V, attention_type=wl["attention"], precision=wl["precision"], chunk_size=B)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = model.to(dev).eval()
+    # synthetic features generated on the device (per-rank seed): resident in HBM before the timed region
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    feats = torch.randn(B, T, F, generator=g, device=dev, dtype=torch.float32)
+    kw = dict(beam_size=K, length_penalty=1.0) if wl["method"] == "beam" else {}
+
+    def step(x):
+        return model.generate(x, START, END, max_length=S, method=wl["method"], **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step(feats)
+    barrier()
+
+    # ---- timed region (device-resident inputs); inputs (1.3 GB at B=1024) far exceed the 126 MB L2
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.25)
+    l0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        out = step(feats)
+        if world > 1:   # the path's only collective: final caption gather (latency-bound)
+            gather_captions(out["generated_tokens"], out["lengths"] if "lengths" in out else
+                            torch.full((B,), out["generated_tokens"].shape[1], device=dev), START)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = _native.launch_count() - l0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e through the public API with host buffers
+    host = torch.empty(B, T, F, dtype=torch.float32).pin_memory()
+    host.copy_(feats.cpu())
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        o = step(host.to(dev, non_blocking=True))
+        _ = o["generated_tokens"].cpu()
+    barrier()
+    e0.record()
+    d2h = 0
+    for _ in range(e2e_steps):
+        o = step(host.to(dev, non_blocking=True))
+        tk = o["generated_tokens"].cpu()
+        d2h = tk.numel() * tk.element_size()
+        if "lengths" in o:
+            ln = o["lengths"].cpu()
+            d2h += ln.numel() * ln.element_size()
+    e1.record()
+    barrier()
+    ems = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(ems.item()) * 1e-3)
+    e2e = {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": int(d2h)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- instrumented pass: per-class device time with CUDA events on the launching stream
+    prof_steps = 2
+    _native.profile_begin()
+    for _ in range(prof_steps):
+        step(feats)
+    prof = _native.profile_end()
+    peaks = load_peaks()
+    work = class_work(wl, cm, B)
+    total_ms = sum(v["ms"] for v in prof.values()) / prof_steps
+    breakdown = {}
+    for cls, v in prof.items():
+        if v["scopes"] == 0:
+            continue
+        cms = v["ms"] / prof_steps
+        wk = work.get(cls, dict(flops=0, bytes=0))
+        ent = {"ms_per_step": cms, "share": cms / total_ms, "launches_per_step": v["scopes"] / prof_steps,
+               "tflops": wk["flops"] / (cms * 1e-3) / 1e12 if cms > 0 else 0.0,
+               "gbs": wk["bytes"] / (cms * 1e-3) / 1e9 if cms > 0 else 0.0}
+        breakdown[cls] = ent
+    dom = max(breakdown, key=lambda c: breakdown[c]["ms_per_step"])
+    d = breakdown[dom]
+    per_launch = d["launches_per_step"]
+    if dom in TENSOR_CLASSES and wl["precision"] == "bf16":
+        # kernels timed inside a long step -> sustained cuBLAS figure
+        roof = {"kernel": dom, "bound": "tensor", "achieved": d["tflops"], "peak": peaks["tf_sus"], "unit": "TFLOP/s",
+                "frac": d["tflops"] / peaks["tf_sus"], "traffic": None,
+                "avg_launch_ms": d["ms_per_step"] / per_launch, "flops_per_launch": work[dom]["flops"] / per_launch}
+    else:
+        roof = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": d["gbs"] / peaks["hbm"], "traffic": None,
+                "avg_launch_ms": d["ms_per_step"] / per_launch, "bytes_per_launch": work[dom]["bytes"] / per_launch}
+    roof["peak_source"] = peaks["source"]
+    roof["share_of_step"] = d["share"]
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v, dt, th = cpu_reference_run(wl, args.cpu_videos)
+        cpu = {"value": v, "unit": "captions/s", "cores": th, "kind": "port",
+               "sample": f"{args.cpu_videos} videos ({dt:.1f} s), oracle port of the reference, one B=1 {wl['method']} call per video"}
+
+    line = {"metric": "captions/sec", "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": wl["precision"], "data": "synthetic",
+            "config": {"workload": args.workload, "videos_per_gpu_per_step": B, "frames": T, "feature_dim": F,
+                       "hidden": cm.encoder_hidden_dim, "vocab": V, "method": wl["method"], "beam": K, "max_len": S,
+                       "attention": wl["attention"], "l2": "inputs (B*T*F*4 bytes) larger than L2, no flush needed",
+                       "sharding": f"dp{world}: videos split over ranks, final NCCL all_gather of tokens"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "breakdown": breakdown}
+    print(json.dumps(line), flush=True)
+    if args.profile_json:
+        with open(args.profile_json, "w") as f:
+            json.dump({"workload": args.workload, "config": line["config"], "ms_per_step": line["ms_per_step"],
+                       "breakdown": breakdown, "roofline": roof, "peaks": peaks}, f, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

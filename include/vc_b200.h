@@ -62,6 +62,31 @@ typedef struct {
 const char* vc_last_error(void);           /* thread-local message for the last non-zero status */
 int vc_version(void);
 
+/* ---- measurement hooks (bench.py).  Kernel classes of the path; every launch is counted, and between
+ * vc_profile_begin/vc_profile_end each class's launches are bracketed with CUDA events on the launching
+ * stream.  vc_profile_end synchronises the device and returns summed milliseconds + scope counts. */
+enum {
+  VC_CLS_CONVERT = 0,           /* fp32 -> bf16 feature cast (bf16 mode only) */
+  VC_CLS_ENC_FEATURE_PROJ = 1,  /* encoder.py:70 */
+  VC_CLS_ENC_INPUT_PROJ = 2,    /* all-timestep W_ih x, both directions */
+  VC_CLS_ENC_RECURRENT = 3,     /* per-timestep h W_hh^T + fused LSTM cell */
+  VC_CLS_ENC_OUTPUT_PROJ = 4,   /* encoder.py:87,96 */
+  VC_CLS_ATTN_PRECOMPUTE = 5,   /* hoisted keys / K,V projections */
+  VC_CLS_ATTN_QUERY_PROJ = 6,
+  VC_CLS_ATTN_STEP = 7,         /* fused score+mask+softmax+context */
+  VC_CLS_ATTN_OUTPUT_PROJ = 8,  /* multi-head output_linear */
+  VC_CLS_DEC_LSTM = 9,          /* decoder LSTM layers: GEMM + fused cell */
+  VC_CLS_DEC_CONTEXT_PROJ = 10, /* decoder.py:164-165 */
+  VC_CLS_DEC_VOCAB = 11,        /* decoder.py:169 */
+  VC_CLS_SELECT = 12,           /* greedy arg-max / beam log-softmax+top-k+select */
+  VC_CLS_REORDER_EMBED = 13,    /* beam state gather + next-token embedding */
+  VC_CLS_MISC = 14,             /* init / finalize / token feeds */
+  VC_CLS_COUNT = 15
+};
+long long vc_launch_count(void);           /* kernels launched by this library in this process so far */
+int vc_profile_begin(void);
+int vc_profile_end(float* ms_per_class /*[VC_CLS_COUNT]*/, int32_t* scopes_per_class /*[VC_CLS_COUNT]*/);
+
 /* ---- model handle: replaces VideoCaptioningModel.__init__ + load_state_dict (video_captioning_model.py:13-33,
  * inference/predictor.py:70-74).  Weights are passed under their reference state_dict keys
  *  as fp32 [numel] arrays (host or device pointers); the handle keeps its own

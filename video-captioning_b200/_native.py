@@ -32,7 +32,7 @@ PRECISION_IDS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 
 # every symbol include/vc_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = (
-    "vc_last_error", "vc_version", "vc_model_create", "vc_model_set_weight", "vc_model_finalize",
+    "vc_last_error", "vc_version", "vc_launch_count", "vc_profile_begin", "vc_profile_end", "vc_model_create", "vc_model_set_weight", "vc_model_finalize",
     "vc_model_destroy", "vc_workspace_bytes", "vc_encoder_forward", "vc_attn_precompute",
     "vc_decode_greedy", "vc_decode_beam", "vc_generate", "vc_forward_teacher", "vc_linear",
     "vc_attention_step", "vc_beam_select",
@@ -94,6 +94,10 @@ def load_library() -> ctypes.CDLL:
         lib.vc_last_error.restype = ctypes.c_char_p
         lib.vc_last_error.argtypes = []
         lib.vc_version.restype = ctypes.c_int
+        lib.vc_launch_count.restype = ctypes.c_longlong
+        lib.vc_launch_count.argtypes = []
+        lib.vc_profile_begin.argtypes = []
+        lib.vc_profile_end.argtypes = [vp, vp]
         lib.vc_model_create.argtypes = [ctypes.POINTER(ModelDesc), ctypes.POINTER(vp)]
         lib.vc_model_set_weight.argtypes = [vp, ctypes.c_char_p, f32p, i64, vp]
         lib.vc_model_finalize.argtypes = [vp, vp]
@@ -113,10 +117,32 @@ def load_library() -> ctypes.CDLL:
         lib.vc_beam_select.argtypes = [f32p, f32p, i32, i32, i32, i32p, i32p, f32p, vp, sz, vp]
         for name in EXPORTED_SYMBOLS:
             fn = getattr(lib, name)
-            if name not in ("vc_last_error", "vc_model_destroy", "vc_workspace_bytes"):
+            if name not in ("vc_last_error", "vc_model_destroy", "vc_workspace_bytes", "vc_launch_count"):
                 fn.restype = ctypes.c_int
         _lib = lib
         return lib
+
+
+KERNEL_CLASSES = ("convert", "enc_feature_proj", "enc_input_proj", "enc_recurrent", "enc_output_proj",
+                  "attn_precompute", "attn_query_proj", "attn_step", "attn_output_proj", "dec_lstm",
+                  "dec_context_proj", "dec_vocab", "select", "reorder_embed", "misc")
+
+
+def launch_count() -> int:
+    return int(load_library().vc_launch_count())
+
+
+def profile_begin() -> None:
+    check(load_library().vc_profile_begin(), "vc_profile_begin")
+
+
+def profile_end() -> Dict[str, Dict[str, float]]:
+    """-> {class: {"ms": summed device milliseconds, "scopes": event-bracketed launch scopes}}"""
+    n = len(KERNEL_CLASSES)
+    ms = (ctypes.c_float * n)()
+    cnt = (ctypes.c_int32 * n)()
+    check(load_library().vc_profile_end(ms, cnt), "vc_profile_end")
+    return {KERNEL_CLASSES[i]: {"ms": float(ms[i]), "scopes": int(cnt[i])} for i in range(n)}
 
 
 def check(status: int, what: str) -> None:

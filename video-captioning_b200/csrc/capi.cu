@@ -31,6 +31,46 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---------------------------------------------------------------- launch accounting + per-class event timing
+// Every kernel launch of the path goes through a LaunchScope: it counts launches (bench.py's
+// `gpu_launches`) and, when profiling is enabled (vc_profile_begin), brackets the launch with CUDA events
+// recorded on the launching stream so bench.py can attribute device time to kernel classes.
+struct Profiler {
+  bool on = false;
+  long long launches = 0;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int cls; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+};
+static Profiler g_prof;
+
+struct LaunchScope {
+  cudaStream_t s;
+  cudaEvent_t b = nullptr;
+  LaunchScope(int cls, cudaStream_t stream, int n = 1) : s(stream) {
+    g_prof.launches += n;
+    if (g_prof.on) {
+      cudaEvent_t a = g_prof.get();
+      b = g_prof.get();
+      cudaEventRecord(a, s);
+      g_prof.recs.push_back({cls, a, b});
+    }
+  }
+  ~LaunchScope() {
+    if (b) cudaEventRecord(b, s);
+  }
+};
+#define VC_SCOPE(cls) vc::LaunchScope _vc_scope_(cls, s)
+
 // ---------------------------------------------------------------- weight preparation kernels
 // dst[rmap(r), dst_col0 + c] = src[r, src_col0 + c];  rmap interleaves LSTM gates: row g*H+u -> 4u+g.
 template <class OutT>
@@ -364,12 +404,16 @@ int run_encoder(vc_model* m, WS<ActT>& w, const float* feats, int B, int T, cons
   // feature projection (:70)
   const void* Ain = feats;
   if (!P) {
+    VC_SCOPE(VC_CLS_CONVERT);
     const int64_t n4 = (int64_t)BT * F / 4;
     convert_f32_to_bf16_kernel<<<(int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16), 256, 0, s>>>(feats, w.feats_bf16, n4);
     VC_CUDA(cudaGetLastError());
     Ain = w.feats_bf16;
   }
-  VC_TRY((gemm<ActT>(gargs(Ain, F, m->Wp, F, BT, H, F), F, estore<ActT, false, P>(w.proj, H, m->bp), s)));
+  {
+    VC_SCOPE(VC_CLS_ENC_FEATURE_PROJ);
+    VC_TRY((gemm<ActT>(gargs(Ain, F, m->Wp, F, BT, H, F), F, estore<ActT, false, P>(w.proj, H, m->bp), s)));
+  }
   VC_CUDA(cudaMemsetAsync(w.zero_h, 0, sizeof(ActT) * (size_t)B * 2 * H, s));
 
   const ActT* layer_in = w.proj;
@@ -378,8 +422,11 @@ int run_encoder(vc_model* m, WS<ActT>& w, const float* feats, int B, int T, cons
   int last_hs = 0;
   for (int l = 0; l < d.enc_layers; ++l) {
     // all-timestep input projections of both directions in one GEMM, N = 8H (:84, nn.LSTM W_ih x + b_ih + b_hh)
-    VC_TRY((gemm<ActT>(gargs(layer_in, in_dim, m->enc_Wih[l], in_dim, BT, 8 * H, in_dim), in_dim,
-                       estore<ActT, false, P>(w.xp, 8 * H, m->enc_bias[l]), s)));
+    {
+      VC_SCOPE(VC_CLS_ENC_INPUT_PROJ);
+      VC_TRY((gemm<ActT>(gargs(layer_in, in_dim, m->enc_Wih[l], in_dim, BT, 8 * H, in_dim), in_dim,
+                         estore<ActT, false, P>(w.xp, 8 * H, m->enc_bias[l]), s)));
+    }
     out = w.out[l & 1];
     VC_CUDA(cudaMemsetAsync(w.cst, 0, sizeof(float) * (size_t)2 * B * H, s));
     if (lengths) VC_CUDA(cudaMemsetAsync(w.hs[0], 0, sizeof(ActT) * (size_t)B * 2 * H, s));
@@ -420,16 +467,21 @@ int run_encoder(vc_model* m, WS<ActT>& w, const float* feats, int B, int T, cons
       e.add_ld = (int64_t)T * 8 * H;
       e.c_ld = H;
       e.h0_ld = (int64_t)T * 2 * H;
+      VC_SCOPE(VC_CLS_ENC_RECURRENT);
       VC_TRY((gemm<ActT>(g, a_cols, e, s)));
     }
     layer_in = out;
     in_dim = 2 * H;
   }
   // output projection over all frames (:87); fp32 copy to the caller if requested
-  VC_TRY((gemm<ActT>(gargs(out, 2 * H, m->Wo, 2 * H, BT, H, 2 * H), 2 * H,
-                     estore<ActT, false, P>(w.enc_act, H, m->bo, P ? nullptr : enc_out_user, H), s)));
+  {
+    VC_SCOPE(VC_CLS_ENC_OUTPUT_PROJ);
+    VC_TRY((gemm<ActT>(gargs(out, 2 * H, m->Wo, 2 * H, BT, H, 2 * H), 2 * H,
+                       estore<ActT, false, P>(w.enc_act, H, m->bo, P ? nullptr : enc_out_user, H), s)));
+  }
   if (P && enc_out_user) VC_CUDA(cudaMemcpyAsync(enc_out_user, w.enc_act, sizeof(float) * (size_t)BT * H, cudaMemcpyDeviceToDevice, s));
   // final state [h_fwd(T-1) ; h_bwd(0)] through the same W_o (:92-96)
+  VC_SCOPE(VC_CLS_ENC_OUTPUT_PROJ);
   if (lengths) {
     VC_TRY((gemm<ActT>(gargs(w.hs[last_hs], 2 * H, m->Wo, 2 * H, B, H, 2 * H), 2 * H,
                        estore<float, false, P>(w.final_f32, H, m->bo), s)));
@@ -450,6 +502,7 @@ int run_precompute(vc_model* m, WS<ActT>& w, int B, int T, cudaStream_t s) {
   constexpr bool P = std::is_same<ActT, float>::value;
   const vc_model_desc_t& d = m->d;
   const int H = d.hidden_dim, A = d.attn_dim, BT = B * T;
+  VC_SCOPE(VC_CLS_ATTN_PRECOMPUTE);
   if (d.attention == VC_ATTN_BAHDANAU || d.attention == VC_ATTN_LUONG_CONCAT) {
     VC_TRY((gemm<ActT>(gargs(w.enc_act, H, m->Wkey, H, BT, A, H), H, estore<ActT, false, P>(w.keys, A, m->bkey), s)));
   } else if (d.attention == VC_ATTN_MULTIHEAD) {
@@ -473,25 +526,44 @@ int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64
   a.B = B; a.K = K; a.T_ = T; a.H = H; a.heads = 1; a.scale = 1.f;
   switch (d.attention) {
     case VC_ATTN_BAHDANAU:
-    case VC_ATTN_LUONG_CONCAT:
-      VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, A, H), hq_cols, estore<float, false, P>(w.Q, A, m->bq), s)));   // attention.py:53 / :138
+    case VC_ATTN_LUONG_CONCAT: {
+      {
+        VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
+        VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, A, H), hq_cols, estore<float, false, P>(w.Q, A, m->bq), s)));   // attention.py:53 / :138
+      }
       a.skeys = w.keys; a.q = w.Q; a.v = m->vvec; a.v_bias = m->vbias; a.D = A;
+      VC_SCOPE(VC_CLS_ATTN_STEP);
       return launch_attn_step<ActT, ATTN_ADDITIVE, P>(a, s);
-    case VC_ATTN_LUONG_DOT:
+    }
+    case VC_ATTN_LUONG_DOT: {
       a.skeys = w.enc_act; a.q_act = hq; a.q_ld = hq_ld; a.D = H;
+      VC_SCOPE(VC_CLS_ATTN_STEP);
       return launch_attn_step<ActT, ATTN_DOT, P>(a, s);
-    case VC_ATTN_LUONG_GENERAL:
-      VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, H, H), hq_cols, estore<float, false, P>(w.Q, H, nullptr), s)));  // :128
+    }
+    case VC_ATTN_LUONG_GENERAL: {
+      {
+        VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
+        VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, H, H), hq_cols, estore<float, false, P>(w.Q, H, nullptr), s)));  // :128
+      }
       a.skeys = w.enc_act; a.q = w.Q; a.D = H;
+      VC_SCOPE(VC_CLS_ATTN_STEP);
       return launch_attn_step<ActT, ATTN_DOT, P>(a, s);
+    }
     case VC_ATTN_MULTIHEAD: {
-      VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, H, H), hq_cols, estore<float, false, P>(w.Q, H, m->bq), s)));    // :240
+      {
+        VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
+        VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, H, H), hq_cols, estore<float, false, P>(w.Q, H, m->bq), s)));    // :240
+      }
       a.skeys = w.keys; a.values = w.vals; a.q = w.Q; a.D = H; a.heads = d.num_heads;
       a.scale = 1.0f / sqrtf((float)(H / d.num_heads));
       a.ctx = w.ctx_pre; a.ctx_ld = H;
-      VC_TRY((launch_attn_step<ActT, ATTN_MHA, P>(a, s)));
+      {
+        VC_SCOPE(VC_CLS_ATTN_STEP);
+        VC_TRY((launch_attn_step<ActT, ATTN_MHA, P>(a, s)));
+      }
       GemmArgs g = gargs(w.ctx_pre, H, m->Wao, H, R, H, H);
       EpiStore<ActT, false, P> e = estore<ActT, false, P>(ctx, ctx_ld, m->bao);                                          // :270
+      VC_SCOPE(VC_CLS_ATTN_OUTPUT_PROJ);
       return gemm<ActT>(g, H, e, s);
     }
   }
@@ -525,9 +597,12 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
   bs.scores = w.scores; bs.alive = w.alive; bs.done = w.done; bs.best_score = w.best_score; bs.best_len = w.best_len;
   bs.best_seq = w.best_seq; bs.hist[0] = w.hist[0]; bs.hist[1] = w.hist[1];
 
-  decode_init_kernel<ActT><<<R, 128, 0, s>>>(st, w.final_f32, R, K, p.start_token_id,
+  {
+    VC_SCOPE(VC_CLS_MISC);
+    decode_init_kernel<ActT><<<R, 128, 0, s>>>(st, w.final_f32, R, K, p.start_token_id,
                                              mode == DM_TEACHER ? teacher_tokens : nullptr, (int64_t)S, w.cur_tok, w.scores,
-                                             w.alive, w.done, w.best_score, w.best_len, p.diverse_beams);
+                                               w.alive, w.done, w.best_score, w.best_len, p.diverse_beams);
+  }
   VC_CUDA(cudaGetLastError());
 
   const ActT* hq = st.x_rec[L - 1];
@@ -554,6 +629,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       e.h0_ld = H;
       if (l < L - 1) { e.h_out1[0] = e.h_out1[1] = w.XL[l + 1]; e.h1_ld = 2 * H; }
       else { e.h_out1[0] = e.h_out1[1] = w.Z + (E + 2 * H); e.h1_ld = ZW; }
+      VC_SCOPE(VC_CLS_DEC_LSTM);
       VC_TRY((gemm<ActT>(g, lda, e, s)));
     }
     // tanh(context_projection([h_top ; ctx ; emb])) (:157-165), operands read in place from Z
@@ -561,18 +637,24 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       GemmArgs g = gargs(w.Z, ZW, m->Wc, 2 * H + E, R, H, 2 * H + E);
       g.a_split = E + H;
       g.a_skip = H;
+      VC_SCOPE(VC_CLS_DEC_CONTEXT_PROJ);
       VC_TRY((gemm<ActT>(g, ZW, estore<ActT, true, P>(w.O, H, m->bc), s)));
     }
     // vocabulary projection (:169)
     float* lg = (mode == DM_TEACHER) ? teacher_logits + (size_t)step * V : w.logits;
     const int64_t ldl = (mode == DM_TEACHER) ? (int64_t)S * V : V;
-    VC_TRY((gemm<ActT>(gargs(w.O, H, m->Wv, H, R, V, H), H, estore<float, false, P>(lg, ldl, m->bv), s)));
+    {
+      VC_SCOPE(VC_CLS_DEC_VOCAB);
+      VC_TRY((gemm<ActT>(gargs(w.O, H, m->Wv, H, R, V, H), H, estore<float, false, P>(lg, ldl, m->bv), s)));
+    }
     // selection
     const int* parent = nullptr;
     if (mode == DM_GREEDY) {
+      VC_SCOPE(VC_CLS_SELECT);
       greedy_argmax_kernel<<<R, 256, 0, s>>>(lg, ldl, V, p.temperature == 1.0f ? 1.f : 0.f, p.temperature, w.cur_tok,
                                              tokens_out, S, step);
     } else if (mode == DM_BEAM) {
+      vc::LaunchScope _sel(VC_CLS_SELECT, s, 2);
       if (K <= 4) beam_row_topk_kernel<4><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
       else if (K <= 8) beam_row_topk_kernel<8><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
       else beam_row_topk_kernel<16><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
@@ -580,15 +662,18 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
                                                       p.length_penalty, w.parent, w.cur_tok);
       parent = w.parent;
     } else if (step + 1 < S) {
+      VC_SCOPE(VC_CLS_MISC);
       set_tokens_kernel<<<(R + 127) / 128, 128, 0, s>>>(w.cur_tok, teacher_tokens, S, step + 1, R);
     }
     VC_CUDA(cudaGetLastError());
     if (step + 1 < S) {
+      VC_SCOPE(VC_CLS_REORDER_EMBED);
       reorder_embed_kernel<ActT><<<R, 128, 0, s>>>(st, parent, w.cur_tok, V);
       VC_CUDA(cudaGetLastError());
     }
   }
   if (mode == DM_BEAM) {
+    VC_SCOPE(VC_CLS_MISC);
     beam_finalize_kernel<<<(B + 63) / 64, 64, 0, s>>>(bs, B, K, S, S, p.start_token_id, tokens_out, lengths_out, scores_out);
     VC_CUDA(cudaGetLastError());
   }
@@ -631,6 +716,31 @@ extern "C" {
 
 const char* vc_last_error(void) { return g_err; }
 int vc_version(void) { return 100; }
+
+long long vc_launch_count(void) { return g_prof.launches; }
+
+int vc_profile_begin(void) {
+  g_prof.on = true;
+  g_prof.used = 0;
+  g_prof.recs.clear();
+  return VC_OK;
+}
+
+int vc_profile_end(float* ms_per_class, int32_t* launches_per_class) {
+  VC_CHECK(ms_per_class != nullptr && launches_per_class != nullptr, "null argument");
+  g_prof.on = false;
+  VC_CUDA(cudaDeviceSynchronize());
+  for (int c = 0; c < VC_CLS_COUNT; ++c) { ms_per_class[c] = 0.f; launches_per_class[c] = 0; }
+  for (const auto& r : g_prof.recs) {
+    float ms = 0.f;
+    VC_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_per_class[r.cls] += ms;
+    launches_per_class[r.cls] += 1;
+  }
+  g_prof.recs.clear();
+  g_prof.used = 0;
+  return VC_OK;
+}
 
 int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   VC_CHECK(desc != nullptr && out != nullptr, "null argument");
