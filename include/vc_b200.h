@@ -130,10 +130,11 @@ int vc_generate(vc_model_t* m, const float* feats, int32_t B, int32_t T, const i
 
 /* ---- teacher-forced forward: VideoCaptioningModel.forward / CaptionDecoder.forward
  * (video_captioning_model.py:35-77, decoder.py:173-221).  input_tokens [B,L] int32;
- * logits [B,L,V]; attn_weights [B,L,T] or NULL.  Workspace as for K=1, S=L. */
+ * logits [B,L,V]; attn_weights [B,L,T] or NULL; enc_out [B,T,H] or NULL ('encoder_outputs' of the
+ * reference's return dict).  Workspace as for K=1, S=L. */
 int vc_forward_teacher(vc_model_t* m, const float* feats, int32_t B, int32_t T, const int32_t* frame_lengths,
                        const float* mask, const int32_t* input_tokens, int32_t L, float* logits, float* attn_weights,
-                       void* workspace, size_t workspace_bytes, vc_stream_t stream);
+                       float* enc_out, void* workspace, size_t workspace_bytes, vc_stream_t stream);
 
 /* ---- step-level entry points used by the parity tests ---------------------------------------- */
 /* C[M,N] = A[M,K] . W[N,K]^T + bias  through the GEMM kernel of the given precision (fp32 FFMA or bf16

@@ -111,7 +111,7 @@ def load_library() -> ctypes.CDLL:
         lib.vc_decode_beam.argtypes = [vp, i32, i32, f32p, ctypes.POINTER(DecodeParams), i32p, i32p, f32p, vp, sz, vp]
         lib.vc_generate.argtypes = [vp, f32p, i32, i32, i32p, f32p, ctypes.POINTER(DecodeParams), i32p, i32p, f32p,
                                     f32p, vp, sz, vp]
-        lib.vc_forward_teacher.argtypes = [vp, f32p, i32, i32, i32p, f32p, i32p, i32, f32p, f32p, vp, sz, vp]
+        lib.vc_forward_teacher.argtypes = [vp, f32p, i32, i32, i32p, f32p, i32p, i32, f32p, f32p, f32p, vp, sz, vp]
         lib.vc_linear.argtypes = [i32, f32p, f32p, f32p, f32p, i32, i32, i32, i32, vp, sz, vp]
         lib.vc_attention_step.argtypes = [vp, f32p, f32p, f32p, i32, i32, i32, f32p, f32p, vp, sz, vp]
         lib.vc_beam_select.argtypes = [f32p, f32p, i32, i32, i32, i32p, i32p, f32p, vp, sz, vp]
@@ -279,12 +279,13 @@ class NativeModel:
         L = tok.shape[1]
         logits = torch.empty(B, L, self.V, dtype=torch.float32, device=self.device)
         attn = torch.empty(B, L, T, dtype=torch.float32, device=self.device) if want_attention else None
+        enc_out = torch.empty(B, T, self.H, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             ws = self._workspace(B, T, 1, L)
             check(self.lib.vc_forward_teacher(self._h, _ptr(f), B, T, _ptr(lengths), _ptr(m), _ptr(tok), L,
-                                              _ptr(logits), _ptr(attn), _ptr(ws), ws.numel(), _stream(self.device)),
-                  "vc_forward_teacher")
-        return logits, attn
+                                              _ptr(logits), _ptr(attn), _ptr(enc_out), _ptr(ws), ws.numel(),
+                                              _stream(self.device)), "vc_forward_teacher")
+        return logits, attn, enc_out
 
     def attention_step(self, enc_out, hidden, mask, K):
         require_cuda(enc_out, "enc_out")

@@ -382,6 +382,7 @@ GemmArgs gargs(const void* A, int64_t lda, const void* W, int64_t ldw, int M, in
   g.W[0] = g.W[1] = W;
   g.lda = lda; g.ldw = ldw; g.M = M; g.N = N; g.K = K; g.nz = 1;
   g.a_col0 = 0; g.a_split = 1 << 30; g.a_skip = 0;
+  g.a_origin = nullptr; g.a_origin_cols = 0;
   return g;
 }
 template <class OutT, bool TANH, bool P>
@@ -452,21 +453,26 @@ int run_encoder(vc_model* m, WS<ActT>& w, const float* feats, int B, int T, cons
       } else if (st == 0) {
         g.A[0] = w.zero_h; g.A[1] = w.zero_h + H;
         g.lda = 2 * H; a_cols = H;
+        g.a_origin = w.zero_h; g.a_origin_cols = 2 * H;
       } else {
         // h_{t-1} is read straight from the layer output buffer [B, T, 2H]
         g.A[0] = out + (size_t)(tz[0] - 1) * 2 * H;
         g.A[1] = out + (size_t)(tz[1] + 1) * 2 * H + H;
         g.lda = (int64_t)T * 2 * H; a_cols = H;
+        g.a_origin = out; g.a_origin_cols = (int64_t)T * 2 * H;
       }
       for (int z = 0; z < 2; ++z) {
         g.W[z] = m->enc_Whh[l][z];
         e.addend[z] = w.xp + (size_t)tz[z] * 8 * H + (size_t)z * 4 * H;
-        e.c_prev[z] = e.c_new[z] = w.cst + (size_t)z * B * H;
+        e.c_prev[z] = e.c_new[z] = w.cst + (size_t)z * H;        // cell state [B, 2H], direction-major columns
         e.h_out0[z] = out + (size_t)tz[z] * 2 * H + (size_t)z * H;
       }
       e.add_ld = (int64_t)T * 8 * H;
-      e.c_ld = H;
+      e.c_ld = 2 * H;
       e.h0_ld = (int64_t)T * 2 * H;
+      e.add_origin = w.xp; e.add_origin_cols = (int64_t)T * 8 * H;
+      e.c_origin_in = e.c_origin_out = w.cst; e.c_tma_cols = 2 * H;
+      e.h0_origin = out; e.h0_origin_cols = (int64_t)T * 2 * H;
       VC_SCOPE(VC_CLS_ENC_RECURRENT);
       VC_TRY((gemm<ActT>(g, a_cols, e, s)));
     }
@@ -476,10 +482,13 @@ int run_encoder(vc_model* m, WS<ActT>& w, const float* feats, int B, int T, cons
   // output projection over all frames (:87); fp32 copy to the caller if requested
   {
     VC_SCOPE(VC_CLS_ENC_OUTPUT_PROJ);
-    VC_TRY((gemm<ActT>(gargs(out, 2 * H, m->Wo, 2 * H, BT, H, 2 * H), 2 * H,
-                       estore<ActT, false, P>(w.enc_act, H, m->bo, P ? nullptr : enc_out_user, H), s)));
+    VC_TRY((gemm<ActT>(gargs(out, 2 * H, m->Wo, 2 * H, BT, H, 2 * H), 2 * H, estore<ActT, false, P>(w.enc_act, H, m->bo), s)));
   }
-  if (P && enc_out_user) VC_CUDA(cudaMemcpyAsync(enc_out_user, w.enc_act, sizeof(float) * (size_t)BT * H, cudaMemcpyDeviceToDevice, s));
+  if (enc_out_user) {
+    VC_SCOPE(VC_CLS_MISC);
+    cast_kernel<ActT, float><<<1184, 256, 0, s>>>(w.enc_act, enc_out_user, (int64_t)BT * H);
+    VC_CUDA(cudaGetLastError());
+  }
   // final state [h_fwd(T-1) ; h_bwd(0)] through the same W_o (:92-96)
   VC_SCOPE(VC_CLS_ENC_OUTPUT_PROJ);
   if (lengths) {
@@ -627,8 +636,14 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       e.c_ld = H;
       e.h_out0[0] = e.h_out0[1] = w.Hn[l];
       e.h0_ld = H;
-      if (l < L - 1) { e.h_out1[0] = e.h_out1[1] = w.XL[l + 1]; e.h1_ld = 2 * H; }
-      else { e.h_out1[0] = e.h_out1[1] = w.Z + (E + 2 * H); e.h1_ld = ZW; }
+      if (l < L - 1) {
+        e.h_out1[0] = e.h_out1[1] = w.XL[l + 1]; e.h1_ld = 2 * H;
+        e.h1_origin = w.XL[l + 1]; e.h1_origin_cols = 2 * H;
+      } else {
+        e.h_out1[0] = e.h_out1[1] = w.Z + (E + 2 * H); e.h1_ld = ZW;
+        e.h1_origin = w.Z; e.h1_origin_cols = ZW;
+      }
+      e.c_origin_in = w.C[l]; e.c_origin_out = w.Cn[l]; e.c_tma_cols = H;
       VC_SCOPE(VC_CLS_DEC_LSTM);
       VC_TRY((gemm<ActT>(g, lda, e, s)));
     }
@@ -655,9 +670,10 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
                                              tokens_out, S, step);
     } else if (mode == DM_BEAM) {
       vc::LaunchScope _sel(VC_CLS_SELECT, s, 2);
-      if (K <= 4) beam_row_topk_kernel<4><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
-      else if (K <= 8) beam_row_topk_kernel<8><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
-      else beam_row_topk_kernel<16><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
+      if (K <= 3) beam_row_topk_kernel<3, P><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
+      else if (K <= 5) beam_row_topk_kernel<5, P><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
+      else if (K <= 8) beam_row_topk_kernel<8, P><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
+      else beam_row_topk_kernel<16, P><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
       beam_select_kernel<<<(B + 63) / 64, 64, 0, s>>>(bs, w.cand_val, w.cand_idx, B, K, V, S, step, p.end_token_id,
                                                       p.length_penalty, w.parent, w.cur_tok);
       parent = w.parent;
@@ -872,12 +888,12 @@ int vc_generate(vc_model_t* m, const float* feats, int32_t B, int32_t T, const i
 }
 
 int vc_forward_teacher(vc_model_t* m, const float* feats, int32_t B, int32_t T, const int32_t* frame_lengths,
-                       const float* mask, const int32_t* input_tokens, int32_t L, float* logits, float* attn, void* ws,
-                       size_t ws_bytes, vc_stream_t stream) {
+                       const float* mask, const int32_t* input_tokens, int32_t L, float* logits, float* attn,
+                       float* enc_out, void* ws, size_t ws_bytes, vc_stream_t stream) {
   VC_CHECK(m != nullptr && feats != nullptr && input_tokens != nullptr && logits != nullptr, "null argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   VC_TRY(check_common(m, B, T, 1, L, ws_bytes, ws));
-  VC_TRY(vc_encoder_forward(m, feats, B, T, frame_lengths, nullptr, nullptr, ws, ws_bytes, stream));
+  VC_TRY(vc_encoder_forward(m, feats, B, T, frame_lengths, enc_out, nullptr, ws, ws_bytes, stream));
   VC_TRY(vc_attn_precompute(m, B, T, ws, ws_bytes, stream));
   vc_decode_params_t p;
   memset(&p, 0, sizeof(p));
@@ -950,9 +966,10 @@ int vc_beam_select(const float* logits, const float* scores, int32_t B, int32_t 
   VC_CUDA(cudaMemcpyAsync(bs.scores, scores, sizeof(float) * R, cudaMemcpyDeviceToDevice, s));
   VC_CUDA(cudaMemsetAsync(bs.alive, 1, R, s));
   VC_CUDA(cudaMemsetAsync(bs.best_len, 0, sizeof(int) * B, s));
-  if (K <= 4) beam_row_topk_kernel<4><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
-  else if (K <= 8) beam_row_topk_kernel<8><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
-  else beam_row_topk_kernel<16><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
+  if (K <= 3) beam_row_topk_kernel<3, true><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
+  else if (K <= 5) beam_row_topk_kernel<5, true><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
+  else if (K <= 8) beam_row_topk_kernel<8, true><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
+  else beam_row_topk_kernel<16, true><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
   beam_select_kernel<<<(B + 63) / 64, 64, 0, s>>>(bs, cand_val, cand_idx, B, K, V, 1, 0, /*end_id=*/-1, 1.0f, parent, token);
   VC_CUDA(cudaGetLastError());
   VC_CUDA(cudaMemcpyAsync(new_scores, bs.scores, sizeof(float) * R, cudaMemcpyDeviceToDevice, s));

@@ -101,86 +101,111 @@ __global__ void __launch_bounds__(256) greedy_argmax_kernel(const float* __restr
 // ---------------------------------------------------------------- beam: per-row log-softmax stats + top-K
 // (video_captioning_model.py:209 log_softmax, first half of :215 topk).  The top-K over the K*V
 // candidates of a video is contained in the union of the per-row top-K, so each row only exports its K
-// best log-probs.  One CTA per row; single pass with an online (max, sum-exp) and a per-thread sorted
-// K-list, then K rounds of block arg-max to merge.  Order: value desc, vocabulary index asc.
+// best log-probs.  One CTA per row, one pass over the logits (HBM-bound: R*V*4 bytes per step):
+// per-thread online (max, sum-exp) + sorted K-list, then shuffle-only merges (lanes -> warp -> CTA).
+// Order everywhere: value desc, vocabulary index asc (ties resolve to the lower index).
 template <int KMAX>
+struct TopList {
+  float v[KMAX];
+  int i[KMAX];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) { v[k] = -INFINITY; i[k] = 0x7fffffff; }
+  }
+  // insert (y, idx); caller guarantees y > v[KMAX-1] or (y == v[KMAX-1] && idx < i[KMAX-1])
+  __device__ __forceinline__ void insert(float y, int idx) {
+    v[KMAX - 1] = y; i[KMAX - 1] = idx;
+#pragma unroll
+    for (int k = KMAX - 1; k > 0; --k) {
+      const bool up = v[k] > v[k - 1] || (v[k] == v[k - 1] && i[k] < i[k - 1]);
+      if (up) {
+        const float a = v[k]; v[k] = v[k - 1]; v[k - 1] = a;
+        const int c = i[k]; i[k] = i[k - 1]; i[k - 1] = c;
+      }
+    }
+  }
+  __device__ __forceinline__ void pop() {
+#pragma unroll
+    for (int k = 0; k < KMAX - 1; ++k) { v[k] = v[k + 1]; i[k] = i[k + 1]; }
+    v[KMAX - 1] = -INFINITY; i[KMAX - 1] = 0x7fffffff;
+  }
+};
+
+// K rounds of warp arg-max over the lanes' list heads; lane `k` ends up holding the k-th best of the warp.
+template <int KMAX>
+__device__ __forceinline__ void warp_merge_topk(TopList<KMAX>& l, int K, int lane, float& out_v, int& out_i) {
+  out_v = -INFINITY; out_i = 0x7fffffff;
+  for (int k = 0; k < K; ++k) {
+    float bv = l.v[0];
+    int bi = l.i[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (l.i[0] == bi && l.v[0] == bv) l.pop();     // indices are unique within a row: exactly one lane pops
+    if (lane == k) { out_v = bv; out_i = bi; }
+  }
+}
+
+template <int KMAX, bool PRECISE>
 __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restrict__ logits, int64_t ld, int V, int K,
                                                             float* __restrict__ cand_val /*[R,K] log-prob*/,
                                                             int* __restrict__ cand_idx /*[R,K]*/) {
   const int r = blockIdx.x;
   const float* row = logits + (int64_t)r * ld;
-  float tv[KMAX];
-  int ti[KMAX];
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) { tv[k] = -INFINITY; ti[k] = 0x7fffffff; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int nwarp = 8;
+  TopList<KMAX> tl;
+  tl.init();
   float m = -INFINITY, s = 0.f;
-  for (int i = threadIdx.x * 4; i < V; i += blockDim.x * 4) {
-    float4 x = *reinterpret_cast<const float4*>(row + i);
-    float v[4] = {x.x, x.y, x.z, x.w};
+  for (int i = threadIdx.x * 4; i < V; i += 256 * 4) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(row + i));
+    const float v[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float y = v[j];
-      if (y > m) { s = s * expf(m - y); m = y; }
-      s += expf(y - m);
-      if (y > tv[KMAX - 1]) {   // strictly greater: earlier (lower) index wins ties inside a thread
-        tv[KMAX - 1] = y; ti[KMAX - 1] = i + j;
-#pragma unroll
-        for (int k = KMAX - 1; k > 0; --k)
-          if (tv[k] > tv[k - 1]) {
-            float a = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = a;
-            int c = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = c;
-          }
+      if (y > m) {
+        s *= PRECISE ? expf(m - y) : __expf(m - y);
+        m = y;
       }
+      s += PRECISE ? expf(y - m) : __expf(y - m);
+      if (y > tl.v[KMAX - 1]) tl.insert(y, i + j);   // strictly greater: the earlier index keeps ties
     }
   }
-  // block log-sum-exp
-  __shared__ float sm[8], ss[8];
-  __shared__ float s_lse;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  float wm = warp_max(m);
-  float wsum = warp_sum(s * expf(m - wm));
+  // log-sum-exp of the row
+  __shared__ float sm[nwarp], ss[nwarp], wv[nwarp][KMAX];
+  __shared__ int wi[nwarp][KMAX];
+  const float wm = warp_max(m);
+  const float wsum = warp_sum(m == -INFINITY ? 0.f : s * (PRECISE ? expf(m - wm) : __expf(m - wm)));
+  float ov;
+  int oi;
+  warp_merge_topk<KMAX>(tl, K, lane, ov, oi);
   if (lane == 0) { sm[warp] = wm; ss[warp] = wsum; }
+  if (lane < K) { wv[warp][lane] = ov; wi[warp][lane] = oi; }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     float M = sm[0];
+#pragma unroll
     for (int w = 1; w < nwarp; ++w) M = fmaxf(M, sm[w]);
     float S = 0.f;
-    for (int w = 0; w < nwarp; ++w) S += ss[w] * expf(sm[w] - M);
-    s_lse = M + logf(S);
-  }
-  // K rounds of block arg-max over the threads' list heads
-  __shared__ float rv[8];
-  __shared__ int ri[8], rt[8];
-  __shared__ int s_winner;
-  int head = 0;
-  for (int k = 0; k < K; ++k) {
-    float bv = (head < KMAX) ? tv[head] : -INFINITY;
-    int bi = (head < KMAX) ? ti[head] : 0x7fffffff;
-    int bt = threadIdx.x;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      int ot = __shfl_xor_sync(0xffffffffu, bt, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bt = ot; }
-    }
-    if (lane == 0) { rv[warp] = bv; ri[warp] = bi; rt[warp] = bt; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < nwarp; ++w)
-        if (rv[w] > bv || (rv[w] == bv && ri[w] < bi)) { bv = rv[w]; bi = ri[w]; bt = rt[w]; }
-      cand_val[(int64_t)r * K + k] = bv - s_lse;    // log_softmax value of the k-th best token
-      cand_idx[(int64_t)r * K + k] = bi;
-      s_winner = bt;
-    }
-    __syncthreads();
-    if (threadIdx.x == s_winner) {
-      // pop: shift the list (KMAX is small)
+    for (int w = 0; w < nwarp; ++w) S += ss[w] * (PRECISE ? expf(sm[w] - M) : __expf(sm[w] - M));
+    const float lse = M + logf(S);
+    // lanes 0..7 adopt warp w's (already sorted) K-list and the 8 lists are merged the same way
+    TopList<KMAX> t2;
+    t2.init();
+    if (lane < nwarp) {
 #pragma unroll
-      for (int q = 0; q < KMAX - 1; ++q) { tv[q] = tv[q + 1]; ti[q] = ti[q + 1]; }
-      tv[KMAX - 1] = -INFINITY; ti[KMAX - 1] = 0x7fffffff;
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) { t2.v[k] = wv[lane][k]; t2.i[k] = wi[lane][k]; }
     }
-    __syncthreads();
+    warp_merge_topk<KMAX>(t2, K, lane, ov, oi);
+    if (lane < K) {
+      cand_val[(int64_t)r * K + lane] = ov - lse;    // log_softmax value of the k-th best token
+      cand_idx[(int64_t)r * K + lane] = oi;
+    }
   }
 }
 

@@ -19,6 +19,10 @@ struct GemmArgs {
   int64_t ldw;
   int M, N, K;
   int nz;             // 1 or 2
+  // TMA hint (bf16 path): A[z] points inside a row of a larger 2D buffer whose row 0 starts at a_origin
+  // and spans a_origin_cols columns (e.g. timestep t of a [B, T*2H] layer output).  nullptr: A[z] is the origin.
+  const void* a_origin;
+  int64_t a_origin_cols;
 };
 
 // ---------------------------------------------------------------- plain store (+bias, +tanh)
@@ -67,6 +71,12 @@ struct EpiLstm {
   int t_of_z[2];
   const ActT* h_prev[2];    // needed only when lengths != nullptr
   int64_t hp_ld;
+  // TMA hints (bf16 staged epilogue): origin (row 0, column 0) and addressable columns of the 2D buffers the
+  // pointers above point into.  c_tma_cols == 0 disables the staged path.
+  const void* add_origin; int64_t add_origin_cols;
+  const void* c_origin_in; const void* c_origin_out; int64_t c_tma_cols;
+  const void* h0_origin; int64_t h0_origin_cols;
+  const void* h1_origin; int64_t h1_origin_cols;
 
   __device__ __forceinline__ void operator()(int z, int row, int col, float (&v)[4]) const {
     const int u = col >> 2;

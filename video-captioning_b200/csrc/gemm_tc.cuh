@@ -1,5 +1,5 @@
 // bf16 tensor-core GEMM for sm_100a: TMA -> 128B-swizzled shared memory -> tcgen05.mma -> TMEM ->
-// tcgen05.ld -> fused epilogue.  Hand-written PTX, no CUTLASS/cuBLAS.
+// tcgen05.ld -> fused epilogue -> swizzled shared-memory staging -> TMA store.  Hand-written PTX.
 //
 //   C[M,N] = A[M,K] . W[N,K]^T   A, W bf16 K-major; fp32 accumulation in TMEM.
 //
@@ -8,11 +8,22 @@
 // thread).  kStages-deep smem ring with full/empty mbarriers; tcgen05.commit releases smem slots and
 // signals the epilogue.  One 128 x BN output tile per CTA, BK = 64 (one 128-byte swizzle atom per row).
 //
+// Epilogue I/O never touches global memory with row-per-thread accesses (32 sectors per request; the
+// round-1a profile showed that pattern and the exposed bias-load latency costing 5-10x the MMA time):
+//   * bias is staged in shared memory while the main loop runs,
+//   * the LSTM epilogue's inputs (all-timestep input-projection tile, previous cell state) are TMA-loaded
+//     into swizzled shared memory at kernel start,
+//   * outputs are written as 16-byte chunks into 128B-swizzled staging boxes (bank-conflict free for
+//     row-per-thread writers) and leave through cp.async.bulk.tensor stores, which also clip M/N tails.
+//
 // Descriptor bit layouts follow the PTX ISA tcgen05 "shared memory descriptor" / "instruction
 // descriptor" tables (cross-checked against cute/arch/mma_sm100_desc.hpp in the image).
 #pragma once
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <string.h>
+
+#include <unordered_map>
 
 #include "gemm_common.cuh"
 
@@ -23,6 +34,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;          // bf16 elements = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
+constexpr int kBoxBytes = BM * 128;   // one 128-row x 128-byte staging box
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -32,9 +44,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded spin: a broken pipeline traps instead of hanging the GPU (gpurun strikes).
+// Bounded spin: a broken pipeline traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -54,6 +67,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -104,30 +127,62 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// 16-byte chunk `c` (0..7) of row `r` inside a 128B-swizzled box
+__device__ __forceinline__ uint32_t swz(uint32_t box, int r, int c) { return box + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+enum { EPI_STORE = 0, EPI_LSTM = 1 };
+
+struct alignas(64) TcMaps {
+  CUtensorMap A[2], W[2];
+  // EPI_STORE: io[0] = C.  EPI_LSTM: io[0] = addend (input projections), io[1] = c_prev, io[2] = c_new,
+  // io[3] = h destination 0, io[4] = h destination 1.
+  CUtensorMap io[5];
+};
 struct TcArgs {
   int M, N, K;
-  int a_col0, a_split, a_skip;
+  int a_col0[2], a_split, a_skip;
+  const float* bias[2];
+  int io_col0[5][2];      // column offset of the tile origin inside each io map, per z
+  int has_h1;
 };
 
-template <int BN, int kStages, int kMinBlocks, class Epi>
+// ---------------------------------------------------------------- the kernel
+// EPI_STORE: OutT = float | bf16, optional tanh.   EPI_LSTM: BN = 256 (64 hidden units per tile),
+// HAS_ADD selects the encoder form (gates += input-projection tile).
+template <int BN, int kStages, int kMinBlocks, int EPI, class OutT, bool TANH, bool HAS_ADD>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                    const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1,
-                    const TcArgs g, const Epi epi) {
+gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs g) {
   constexpr uint32_t kABytes = BM * BK * 2;
   constexpr uint32_t kBBytes = BN * BK * 2;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr int kAddBoxes = (EPI == EPI_LSTM && HAS_ADD) ? BN * 2 / 128 : 0;   // bf16 input-projection tile
+  constexpr int kCBoxes = (EPI == EPI_LSTM) ? (BN / 4) * 4 / 128 : 0;          // fp32 cell-state tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* io_smem = smem + (size_t)kStages * kStageBytes;          // [kAddBoxes + kCBoxes] boxes
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t in_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float bias_s[BN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int z = blockIdx.z;
-  const CUtensorMap* mapA = z ? &mapA1 : &mapA0;
-  const CUtensorMap* mapW = z ? &mapW1 : &mapW0;
+  const CUtensorMap* mapA = &maps.A[z];
+  const CUtensorMap* mapW = &maps.W[z];
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int nkb = g.K / BK;
 
@@ -137,6 +192,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(&tmem_full_bar), 1);
+    mbar_init(smem_u32(&in_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(mapW) : "memory");
@@ -150,13 +206,23 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      if (EPI == EPI_LSTM) {
+        // epilogue inputs first: they are resident long before the accumulator is
+        const uint32_t ib = smem_u32(&in_bar);
+        mbar_expect_tx(ib, (uint32_t)(kAddBoxes + kCBoxes) * kBoxBytes);
+        for (int i = 0; i < kAddBoxes; ++i)
+          tma_load_2d(smem_u32(io_smem + (size_t)i * kBoxBytes), &maps.io[0], ib, g.io_col0[0][z] + n0 + i * 64, m0);
+        for (int i = 0; i < kCBoxes; ++i)
+          tma_load_2d(smem_u32(io_smem + (size_t)(kAddBoxes + i) * kBoxBytes), &maps.io[1], ib,
+                      g.io_col0[1][z] + n0 / 4 + i * 32, m0);
+      }
       uint32_t stage = 0, phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t fb = smem_u32(&full_bar[stage]);
         mbar_expect_tx(fb, kStageBytes);
         const int k = kb * BK;
-        const int acol = g.a_col0 + k + (k >= g.a_split ? g.a_skip : 0);
+        const int acol = g.a_col0[z] + k + (k >= g.a_split ? g.a_skip : 0);
         uint8_t* sa = smem + (size_t)stage * kStageBytes;
         tma_load_2d(smem_u32(sa), mapA, fb, acol, m0);
         tma_load_2d(smem_u32(sa + kABytes), mapW, fb, k, n0);
@@ -182,10 +248,219 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         umma_commit(smem_u32(&empty_bar[stage]));   // frees the smem slot when these MMAs retire
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(smem_u32(&tmem_full_bar));         // accumulator complete
+      umma_commit(smem_u32(&tmem_full_bar));         // accumulator complete (all smem reads retired)
     }
   } else {
     // ===== epilogue: warp (warp % 4) owns TMEM lanes [32*(warp%4), +32) = output rows =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                     // row inside the tile
+    const int et = threadIdx.x - 64;                 // 0..127 among the epilogue threads
+    // stage the bias while the main loop runs
+    for (int i = et; i < BN; i += 128) {
+      const int col = n0 + i;
+      bias_s[i] = (g.bias[z] != nullptr && col < g.N) ? g.bias[z][col] : 0.f;
+    }
+    epi_bar_sync();
+    if (nkb > 0) {
+      mbar_wait(smem_u32(&tmem_full_bar), 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    // After tmem_full every MMA (hence every read of the stage buffers) has retired: reuse them as staging.
+    const uint32_t stg = smem_u32(smem);
+
+    if (EPI == EPI_STORE) {
+      constexpr int kColsPerBox = 128 / (int)sizeof(OutT);          // 32 (fp32) or 64 (bf16)
+      constexpr int kLdPerBox = kColsPerBox / 32;
+#pragma unroll 1
+      for (int bx = 0; bx < BN / kColsPerBox; ++bx) {
+        const uint32_t box = stg + (uint32_t)bx * kBoxBytes;
+#pragma unroll
+        for (int h = 0; h < kLdPerBox; ++h) {
+          const int c = bx * kColsPerBox + h * 32;
+          uint32_t v[32];
+          if (nkb > 0) {
+            tmem_ld32(taddr + (uint32_t)c, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f[j] = __uint_as_float(v[j]) + bias_s[c + j];
+            if (TANH) f[j] = tanh_<false>(f[j]);
+          }
+          if (sizeof(OutT) == 4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(swz(box, r, j), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                     __float_as_uint(f[4 * j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128(swz(box, r, h * 4 + j), pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                     pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+          }
+        }
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (et == 0) {
+          const int col = n0 + bx * kColsPerBox;
+          if (col < g.N) tma_store_2d(&maps.io[0], box, g.io_col0[0][z] + col, m0);
+          tma_store_commit();
+        }
+      }
+      if (et == 0) tma_store_wait_read();
+    } else {
+      // ---- fused LSTM cell: 8 hidden units (32 gate columns) per TMEM load
+      constexpr int kUnits = BN / 4;                                 // 64
+      const uint32_t add_s = smem_u32(io_smem);
+      const uint32_t c_s = smem_u32(io_smem + (size_t)kAddBoxes * kBoxBytes);
+      const uint32_t h_box = stg;                                    // 64 units x bf16 = 128B rows
+      mbar_wait(smem_u32(&in_bar), 0);
+#pragma unroll 1
+      for (int ci = 0; ci < BN / 32; ++ci) {
+        const int c = ci * 32;
+        uint32_t v[32];
+        if (nkb > 0) {
+          tmem_ld32(taddr + (uint32_t)c, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        float gte[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) gte[j] = __uint_as_float(v[j]) + bias_s[c + j];
+        if (HAS_ADD) {
+          // 32 bf16 = 4 chunks of the addend box (64 columns per box)
+          const uint32_t abox = add_s + (uint32_t)(c / 64) * kBoxBytes;
+          const int ch0 = (c % 64) / 8;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w0, w1, w2, w3;
+            lds128(swz(abox, r, ch0 + j), w0, w1, w2, w3);
+            gte[8 * j + 0] += bf16_lo(w0); gte[8 * j + 1] += bf16_hi(w0);
+            gte[8 * j + 2] += bf16_lo(w1); gte[8 * j + 3] += bf16_hi(w1);
+            gte[8 * j + 4] += bf16_lo(w2); gte[8 * j + 5] += bf16_hi(w2);
+            gte[8 * j + 6] += bf16_lo(w3); gte[8 * j + 7] += bf16_hi(w3);
+          }
+        }
+        // previous cell state of units u0..u0+7 (fp32, 32 units per box)
+        const int u0 = ci * 8;
+        const uint32_t cbox = c_s + (uint32_t)(u0 / 32) * kBoxBytes;
+        const int cch = (u0 % 32) / 4;
+        uint32_t cw[8];
+        lds128(swz(cbox, r, cch), cw[0], cw[1], cw[2], cw[3]);
+        lds128(swz(cbox, r, cch + 1), cw[4], cw[5], cw[6], cw[7]);
+        float hn[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float ig = sigmoid_<false>(gte[4 * u + 0]);
+          const float fg = sigmoid_<false>(gte[4 * u + 1]);
+          const float gg = tanh_<false>(gte[4 * u + 2]);
+          const float og = sigmoid_<false>(gte[4 * u + 3]);
+          const float cn = fmaf(fg, __uint_as_float(cw[u]), ig * gg);
+          hn[u] = og * tanh_<false>(cn);
+          cw[u] = __float_as_uint(cn);
+        }
+        sts128(swz(cbox, r, cch), cw[0], cw[1], cw[2], cw[3]);          // c_new in place
+        sts128(swz(cbox, r, cch + 1), cw[4], cw[5], cw[6], cw[7]);
+        sts128(swz(h_box, r, ci), pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]),
+               pack_bf16(hn[6], hn[7]));
+      }
+      fence_proxy_async_smem();
+      epi_bar_sync();
+      if (et == 0) {
+        const int u_tile = n0 / 4;
+        tma_store_2d(&maps.io[3], h_box, g.io_col0[3][z] + u_tile, m0);
+        if (g.has_h1) tma_store_2d(&maps.io[4], h_box, g.io_col0[4][z] + u_tile, m0);
+        for (int i = 0; i < kCBoxes; ++i)
+          tma_store_2d(&maps.io[2], c_s + (uint32_t)i * kBoxBytes, g.io_col0[2][z] + u_tile + i * 32, m0);
+        tma_store_commit();
+        tma_store_wait_read();
+      }
+      (void)kUnits;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---------------------------------------------------------------- legacy direct-store kernel
+// Generic functor epilogue with row-per-thread global accesses: slow, kept only for the cases the staged
+// epilogue does not cover (packed-sequence masking, a second fp32 output, unaligned pitches).
+template <int BN, int kStages, int kMinBlocks, class Epi>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+gemm_tc_direct_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, const Epi epi) {
+  constexpr uint32_t kABytes = BM * BK * 2;
+  constexpr uint32_t kBBytes = BN * BK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.z;
+  const CUtensorMap* mapA = &maps.A[z];
+  const CUtensorMap* mapW = &maps.W[z];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb = g.K / BK;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(fb, kStageBytes);
+        const int k = kb * BK;
+        const int acol = g.a_col0[z] + k + (k >= g.a_split ? g.a_skip : 0);
+        uint8_t* sa = smem + (size_t)stage * kStageBytes;
+        tma_load_2d(smem_u32(sa), mapA, fb, acol, m0);
+        tma_load_2d(smem_u32(sa + kABytes), mapW, fb, k, n0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        uint8_t* sa = smem + (size_t)stage * kStageBytes;
+        const uint64_t da = make_smem_desc(smem_u32(sa));
+        const uint64_t db = make_smem_desc(smem_u32(sa + kABytes));
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit(smem_u32(&empty_bar[stage]));
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(smem_u32(&tmem_full_bar));
+    }
+  } else {
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
     if (nkb > 0) {
@@ -223,7 +498,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   }
 }
 
-// ---------------------------------------------------------------- host side: tensor maps
+// ---------------------------------------------------------------- host side: tensor maps (cached)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -240,60 +515,182 @@ inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2D bf16 row-major [rows, cols] with row pitch ld (elements); box = box_rows x 64, 128B swizzle.
-inline int make_map_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+struct MapKey {
+  const void* base; uint64_t rows, cols, ld; uint32_t box_rows, box_cols, esize;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols && esize == o.esize;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
+    mix(k.rows); mix(k.cols); mix(k.ld); mix(k.box_rows); mix(k.box_cols); mix(k.esize);
+    return h;
+  }
+};
+
+// 2D row-major [rows, cols] (elements of esize bytes: 2 = bf16, 4 = fp32) with row pitch ld; box =
+// box_rows x box_cols with box_cols*esize == 128 bytes, 128B swizzle.  Encodes are cached per thread:
+// the decode loop re-uses the same few dozen maps for every step.
+inline int get_map(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                   uint32_t esize) {
+  static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const uint32_t box_cols = 128 / esize;
+  MapKey key{base, rows, cols, ld, box_rows, box_cols, esize};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return VC_OK;
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return VC_ERR_CUDA;
   }
-  VC_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0,
+  VC_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * esize) % 16 == 0,
            "TMA operand must be 16B aligned with a 16B-multiple pitch (ptr=%p ld=%llu)", base, (unsigned long long)ld);
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint64_t strides[1] = {ld * esize};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUtensorMap m;
+  CUresult r = fn(&m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)r, (unsigned long long)rows,
-              (unsigned long long)cols, (unsigned long long)ld);
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu esize=%u", (int)r, (unsigned long long)rows,
+              (unsigned long long)cols, (unsigned long long)ld, esize);
     return VC_ERR_CUDA;
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return VC_OK;
+}
+
+// A buffer reference for TMA: `ptr` may point inside a row of a larger 2D buffer whose row 0 starts at
+// `origin` (nullptr -> ptr is the origin) and has `cols` addressable columns from origin.
+struct Ref {
+  const void* ptr; const void* origin; int64_t cols; int64_t ld;
+};
+inline int ref_map(CUtensorMap* out, int* col0, const Ref& r, uint64_t rows, uint32_t box_rows, uint32_t esize) {
+  const char* o = reinterpret_cast<const char*>(r.origin ? r.origin : r.ptr);
+  *col0 = (int)((reinterpret_cast<const char*>(r.ptr) - o) / esize);
+  return get_map(out, o, rows, (uint64_t)r.cols, (uint64_t)r.ld, box_rows, esize);
+}
+
+inline bool tma_ok(const void* p, int64_t ld, int esize) {
+  return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * esize) % 16 == 0;
+}
+
+inline int fill_ab(TcMaps& mp, TcArgs& ta, const GemmArgs& g, int64_t a_cols, int BN) {
+  VC_CHECK(g.K % BK == 0, "bf16 tensor-core GEMM needs K %% 64 == 0 (K=%d)", g.K);
+  VC_CHECK(g.N % 4 == 0, "bf16 tensor-core GEMM needs N %% 4 == 0 (N=%d)", g.N);
+  VC_CHECK(g.a_col0 % 8 == 0 && g.a_split % BK == 0 && g.a_skip % 8 == 0, "A column offsets must be multiples of 8/64");
+  memset(&ta, 0, sizeof(ta));
+  ta.M = g.M; ta.N = g.N; ta.K = g.K; ta.a_split = g.a_split; ta.a_skip = g.a_skip;
+  for (int z = 0; z < 2; ++z) {
+    const int zz = z < g.nz ? z : 0;
+    int c0 = 0;
+    Ref ra{g.A[zz], g.a_origin, g.a_origin ? g.a_origin_cols : a_cols, g.lda};
+    VC_TRY(ref_map(&mp.A[z], &c0, ra, (uint64_t)g.M, BM, 2));
+    ta.a_col0[z] = c0 + g.a_col0;
+    VC_TRY(get_map(&mp.W[z], g.W[zz], (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, (uint32_t)BN, 2));
   }
   return VC_OK;
 }
 
-// A operand: `a_cols` = number of addressable columns in a row of the A buffer (>= a_col0 + K + a_skip).
 template <class Epi>
-int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const Epi& epi, cudaStream_t stream) {
-  VC_CHECK(g.K % BK == 0, "bf16 tensor-core GEMM needs K %% 64 == 0 (K=%d)", g.K);
-  VC_CHECK(g.N % 4 == 0, "bf16 tensor-core GEMM needs N %% 4 == 0 (N=%d)", g.N);
-  VC_CHECK(g.a_col0 % 8 == 0 && g.a_split % BK == 0 && g.a_skip % 8 == 0, "A column offsets must be multiples of 8/64");
+int launch_direct(const GemmArgs& g, int64_t a_cols, const Epi& epi, cudaStream_t stream) {
+  TcMaps mp;
+  TcArgs ta;
+  VC_TRY(fill_ab(mp, ta, g, a_cols, 128));
+  constexpr int kStages = 3;
+  const size_t smem = (size_t)kStages * (BM * BK * 2 + 128 * BK * 2) + 1024;
+  auto kern = gemm_tc_direct_kernel<128, kStages, 2, Epi>;
+  VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((g.N + 127) / 128, (g.M + BM - 1) / BM, g.nz);
+  kern<<<grid, kThreads, smem, stream>>>(mp, ta, epi);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ---- plain store (+bias, +tanh)
+template <class OutT, bool TANH>
+int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH, false>& e, cudaStream_t stream) {
   if (g.M == 0 || g.N == 0) return VC_OK;
-  CUtensorMap ma[2], mw[2];
-  const int BN = (g.N >= 256 && ((int64_t)((g.M + 127) / 128) * ((g.N + 255) / 256) * g.nz >= 148)) ? 256 : 128;
-  for (int z = 0; z < 2; ++z) {
-    const int zz = z < g.nz ? z : 0;
-    VC_TRY(make_map_bf16(&ma[z], g.A[zz], (uint64_t)g.M, (uint64_t)a_cols, (uint64_t)g.lda, BM));
-    VC_TRY(make_map_bf16(&mw[z], g.W[zz], (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, (uint32_t)BN));
-  }
-  TcArgs ta{g.M, g.N, g.K, g.a_col0, g.a_split, g.a_skip};
+  if (e.C2[0] != nullptr || g.nz != 1 || !tma_ok(e.C[0], e.ldc, sizeof(OutT))) return launch_direct(g, a_cols, e, stream);
+  TcMaps mp;
+  TcArgs ta;
+  const int64_t tiles256 = (int64_t)((g.M + 127) / 128) * ((g.N + 255) / 256);
+  const int BN = (g.N >= 256 && tiles256 >= 148) ? 256 : 128;
+  VC_TRY(fill_ab(mp, ta, g, a_cols, BN));
+  ta.bias[0] = ta.bias[1] = e.bias[0];
+  VC_TRY(get_map(&mp.io[0], e.C[0], (uint64_t)g.M, (uint64_t)g.N, (uint64_t)e.ldc, BM, sizeof(OutT)));
   if (BN == 256) {
     constexpr int kStages = 4;
     const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 1024;
-    auto kern = gemm_bf16_tc_kernel<256, kStages, 1, Epi>;
+    auto kern = gemm_tc_kernel<256, kStages, 1, EPI_STORE, OutT, TANH, false>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((g.N + 255) / 256, (g.M + BM - 1) / BM, g.nz);
-    kern<<<grid, kThreads, smem, stream>>>(ma[0], ma[1], mw[0], mw[1], ta, epi);
+    dim3 grid((g.N + 255) / 256, (g.M + BM - 1) / BM, 1);
+    kern<<<grid, kThreads, smem, stream>>>(mp, ta);
   } else {
     // 3 stages x 32 KB: two CTAs co-reside per SM, so one CTA's epilogue overlaps the other's main loop
     constexpr int kStages = 3;
     const size_t smem = (size_t)kStages * (BM * BK * 2 + 128 * BK * 2) + 1024;
-    auto kern = gemm_bf16_tc_kernel<128, kStages, 2, Epi>;
+    auto kern = gemm_tc_kernel<128, kStages, 2, EPI_STORE, OutT, TANH, false>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((g.N + 127) / 128, (g.M + BM - 1) / BM, g.nz);
-    kern<<<grid, kThreads, smem, stream>>>(ma[0], ma[1], mw[0], mw[1], ta, epi);
+    dim3 grid((g.N + 127) / 128, (g.M + BM - 1) / BM, 1);
+    kern<<<grid, kThreads, smem, stream>>>(mp, ta);
+  }
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ---- fused LSTM cell
+inline int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiLstm<bf16, bf16, false>& e, cudaStream_t stream) {
+  if (g.M == 0 || g.N == 0) return VC_OK;
+  const int H = g.N / 4;
+  const bool staged = e.lengths == nullptr && g.N % 256 == 0 && e.c_tma_cols > 0;
+  if (!staged) return launch_direct(g, a_cols, e, stream);
+  TcMaps mp;
+  TcArgs ta;
+  VC_TRY(fill_ab(mp, ta, g, a_cols, 256));
+  const bool has_add = e.addend[0] != nullptr;
+  for (int z = 0; z < 2; ++z) {
+    const int zz = z < g.nz ? z : 0;
+    ta.bias[z] = e.bias[zz];
+    if (has_add) {
+      Ref r{e.addend[zz], e.add_origin, e.add_origin_cols, e.add_ld};
+      VC_TRY(ref_map(&mp.io[0], &ta.io_col0[0][z], r, (uint64_t)g.M, BM, 2));
+    }
+    Ref rc{e.c_prev[zz], e.c_origin_in, e.c_tma_cols, e.c_ld};
+    VC_TRY(ref_map(&mp.io[1], &ta.io_col0[1][z], rc, (uint64_t)g.M, BM, 4));
+    Ref rn{e.c_new[zz], e.c_origin_out, e.c_tma_cols, e.c_ld};
+    VC_TRY(ref_map(&mp.io[2], &ta.io_col0[2][z], rn, (uint64_t)g.M, BM, 4));
+    Ref rh{e.h_out0[zz], e.h0_origin, e.h0_origin ? e.h0_origin_cols : (int64_t)H, e.h0_ld};
+    VC_TRY(ref_map(&mp.io[3], &ta.io_col0[3][z], rh, (uint64_t)g.M, BM, 2));
+    if (e.h_out1[zz] != nullptr) {
+      Ref r1{e.h_out1[zz], e.h1_origin, e.h1_origin ? e.h1_origin_cols : (int64_t)H, e.h1_ld};
+      VC_TRY(ref_map(&mp.io[4], &ta.io_col0[4][z], r1, (uint64_t)g.M, BM, 2));
+      ta.has_h1 = 1;
+    }
+  }
+  dim3 grid(g.N / 256, (g.M + BM - 1) / BM, g.nz);
+  if (has_add) {
+    constexpr int kStages = 2;
+    const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + (size_t)(4 + 2) * kBoxBytes + 1024;
+    auto kern = gemm_tc_kernel<256, kStages, 1, EPI_LSTM, bf16, false, true>;
+    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, stream>>>(mp, ta);
+  } else {
+    constexpr int kStages = 3;
+    const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + (size_t)2 * kBoxBytes + 1024;
+    auto kern = gemm_tc_kernel<256, kStages, 1, EPI_LSTM, bf16, false, false>;
+    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, stream>>>(mp, ta);
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;

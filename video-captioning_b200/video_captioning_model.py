@@ -152,8 +152,7 @@ class VideoCaptioningModel(nn.Module):
     def forward(self, video_features, input_tokens, target_tokens, video_mask=None) -> Dict[str, torch.Tensor]:
         """Teacher-forced forward, video_captioning_model.py:35-77 (inference only: no autograd graph)."""
         h = self._handle()
-        logits, attn = h.forward_teacher(video_features, input_tokens, video_mask)
-        enc_out, _ = h.encoder_forward(video_features, video_mask)
+        logits, attn, enc_out = h.forward_teacher(video_features, input_tokens, video_mask)
         return {"logits": logits, "encoder_outputs": enc_out, "attention_weights": attn, "target_tokens": target_tokens}
 
     def get_trainable_parameters(self) -> int:
