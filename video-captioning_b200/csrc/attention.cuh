@@ -21,6 +21,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vc {
@@ -29,8 +31,9 @@ enum AttnMode : int { ATTN_ADDITIVE = 0, ATTN_DOT = 1, ATTN_MHA = 2 };
 
 template <class T>
 struct AttnArgs {
-  // scoring operand per video: [B,T,D] (additive: projected keys, D=A; dot: enc_out, D=H; mha: K, D=H)
-  const T* skeys;
+  // scoring operand per video: [B,T,D] (additive: projected keys, D=A; dot: enc_out, D=H; mha: K, D=H).
+  // Element type KT of the kernel: T, except fp16 for the additive form in bf16 mode (packed half2 math).
+  const void* skeys;
   // value operand per video: [B,T,H] (enc_out; mha: V)
   const T* values;
   const float* q;        // [R, D] fp32 query (projected); nullptr when q_act is used
@@ -68,44 +71,130 @@ __device__ __forceinline__ float additive8(const float (&e)[8], const float* __r
   return s;
 }
 
+// Packed fp16 form: sum over 8 elements of v * tanh(key + q), operands as 4 half2 words each.
+// 4 HADD2 + 4 MUFU.TANH(f16x2) + 4 HFMA2, the 4-term half2 partial is then widened to fp32.
+__device__ __forceinline__ float additive8_h2(const uint4& key, const uint4& q, const uint4& v) {
+  const uint32_t kw[4] = {key.x, key.y, key.z, key.w};
+  const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+  const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+  __half2 acc = __float2half2_rn(0.f);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    __half2 x = __hadd2(*reinterpret_cast<const __half2*>(&kw[p]), *reinterpret_cast<const __half2*>(&qw[p]));
+    uint32_t xi = *reinterpret_cast<uint32_t*>(&x), yi;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(yi) : "r"(xi));
+    acc = __hfma2(*reinterpret_cast<const __half2*>(&vw[p]), *reinterpret_cast<__half2*>(&yi), acc);
+  }
+  const float2 f = __half22float2(acc);
+  return f.x + f.y;
+}
+
 constexpr int kAttnThreads = 256;
 constexpr int kAttnFR = 2;   // frames per warp iteration
 
 // KMAX: compile-time bound on beams handled per CTA (K <= KMAX).
-template <class T, int MODE, int KMAX, bool PRECISE>
+// NCH > 0 selects the register-resident scoring loop of the packed additive form: K == KMAX exactly and
+// D <= 256*NCH; every lane keeps its NCH 16-byte chunks of all K queries and of v in registers for the
+// whole kernel, so the frame loop is LDG(key) + HADD2/MUFU/HFMA2 only.
+template <class T, class KT, int MODE, int KMAX, bool PRECISE, int NCH>
 __global__ void __launch_bounds__(kAttnThreads) attn_step_kernel(const AttnArgs<T> a) {
+  constexpr bool PACKED = (MODE == ATTN_ADDITIVE) && std::is_same<KT, __half>::value;   // q, v staged as fp16
+  static_assert(NCH == 0 || PACKED, "register-resident scoring is implemented for the packed additive form");
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.x;
   const int K = a.K, Tn = a.T_, D = a.D, H = a.H;
   const int NH = (MODE == ATTN_MHA) ? a.heads : 1;
   const int dh = D / NH;                                   // scoring columns per head
-  float* q_s = smem;                                       // [K][D]
+  float* q_s = smem;                                       // [K][D] fp32 (PACKED: fp16 in the same space)
   float* v_s = q_s + (size_t)K * D;                        // [D] (additive only)
   float* sc = v_s + ((MODE == ATTN_ADDITIVE) ? D : 0);     // [K][NH][Tn]
   float* red = sc + (size_t)K * NH * Tn;                   // [G][K][H] context partials
+  __half* q_h = reinterpret_cast<__half*>(q_s);
+  __half* v_h = reinterpret_cast<__half*>(v_s);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int nwarp = kAttnThreads / 32;
 
   for (int i = tid; i < K * D; i += kAttnThreads) {
     const int k = i / D, d = i - k * D;
     const int64_t r = (int64_t)b * K + k;
-    q_s[i] = a.q ? a.q[r * D + d] : to_float(a.q_act[r * a.q_ld + d]);
+    const float qv = a.q ? a.q[r * D + d] : to_float(a.q_act[r * a.q_ld + d]);
+    if (PACKED) q_h[i] = __float2half_rn(qv);
+    else q_s[i] = qv;
   }
   if (MODE == ATTN_ADDITIVE)
-    for (int i = tid; i < D; i += kAttnThreads) v_s[i] = a.v[i];
+    for (int i = tid; i < D; i += kAttnThreads) {
+      if (PACKED) v_h[i] = __float2half_rn(a.v[i]);
+      else v_s[i] = a.v[i];
+    }
   if (MODE == ATTN_MHA)
     for (int i = tid; i < K * NH * Tn; i += kAttnThreads) sc[i] = 0.f;
   __syncthreads();
 
   // ---- scores
-  const T* sk = a.skeys + (int64_t)b * Tn * D;
+  const KT* sk = reinterpret_cast<const KT*>(a.skeys) + (int64_t)b * Tn * D;
   const int group = (MODE == ATTN_MHA) ? min(32, dh / 8) : 32;   // lanes reducing together (one head)
+  if constexpr (NCH > 0) {
+    uint4 qreg[KMAX][NCH], vreg[NCH];
+    bool live[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int d0 = lane * 8 + 256 * c;
+      live[c] = d0 < D;
+      vreg[c] = live[c] ? *reinterpret_cast<const uint4*>(v_h + d0) : make_uint4(0, 0, 0, 0);   // v = 0: no contribution
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        qreg[k][c] = live[c] ? *reinterpret_cast<const uint4*>(q_h + k * D + d0) : make_uint4(0, 0, 0, 0);
+    }
+    uint4 key[NCH], nxt[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      key[c] = (live[c] && warp < Tn) ? *reinterpret_cast<const uint4*>(sk + (int64_t)warp * D + lane * 8 + 256 * c)
+                                      : make_uint4(0, 0, 0, 0);
+    for (int t = warp; t < Tn; t += nwarp) {
+      const int tn = t + nwarp;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)   // prefetch the next frame of this warp
+        nxt[c] = (live[c] && tn < Tn) ? *reinterpret_cast<const uint4*>(sk + (int64_t)tn * D + lane * 8 + 256 * c)
+                                      : make_uint4(0, 0, 0, 0);
+      float part[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        float p = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) p += additive8_h2(key[c], qreg[k][c], vreg[c]);
+        part[k] = p;
+      }
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const float sres = warp_sum(part[k]);
+        if (lane == 0) sc[(size_t)k * Tn + t] = sres + a.v_bias;
+      }
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) key[c] = nxt[c];
+    }
+  } else
   for (int t0 = warp * kAttnFR; t0 < Tn; t0 += nwarp * kAttnFR) {
     float part[kAttnFR][KMAX];
 #pragma unroll
     for (int f = 0; f < kAttnFR; ++f)
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) part[f][k] = 0.f;
+    if constexpr (PACKED) {
+      for (int d0 = lane * 8; d0 < D; d0 += 256) {
+        uint4 key[kAttnFR];
+#pragma unroll
+        for (int f = 0; f < kAttnFR; ++f)
+          key[f] = (t0 + f < Tn) ? *reinterpret_cast<const uint4*>(sk + (int64_t)(t0 + f) * D + d0) : make_uint4(0, 0, 0, 0);
+        const uint4 v8 = *reinterpret_cast<const uint4*>(v_h + d0);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) {
+            const uint4 q8 = *reinterpret_cast<const uint4*>(q_h + k * D + d0);
+#pragma unroll
+            for (int f = 0; f < kAttnFR; ++f) part[f][k] += additive8_h2(key[f], q8, v8);
+          }
+      }
+    } else
     for (int d0 = lane * 8; d0 < D || (MODE == ATTN_MHA && d0 - lane * 8 < D); d0 += 256) {
       const bool live = d0 < D;
       float e[kAttnFR][8];
@@ -265,7 +354,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_step_kernel(const AttnArgs<
   }
 }
 
-template <class T, int MODE, bool PRECISE>
+// KT: element type of a.skeys (see AttnArgs)
+template <class T, class KT, int MODE, bool PRECISE>
 int launch_attn_step(const AttnArgs<T>& a, cudaStream_t stream) {
   VC_CHECK(a.K >= 1 && a.K <= 16, "attention: beam size %d not in [1,16]", a.K);
   VC_CHECK(a.H % 8 == 0 && a.D % 8 == 0, "attention: dims must be multiples of 8 (D=%d H=%d)", a.D, a.H);
@@ -280,17 +370,33 @@ int launch_attn_step(const AttnArgs<T>& a, cudaStream_t stream) {
   const size_t smem = sizeof(float) * ((size_t)a.K * a.D + (MODE == ATTN_ADDITIVE ? a.D : 0) + (size_t)a.K * NH * a.T_ +
                                        (G > 1 ? (size_t)G * a.K * a.H : 0));
   VC_CHECK(smem <= 200 * 1024, "attention: K=%d D=%d T=%d needs %zu B shared memory", a.K, a.D, a.T_, smem);
-#define VC_ATTN_LAUNCH(KM)                                                                               \
+#define VC_ATTN_LAUNCH(KM, NC)                                                                           \
   do {                                                                                                   \
-    auto kern = attn_step_kernel<T, MODE, KM, PRECISE>;                                                  \
+    auto kern = attn_step_kernel<T, KT, MODE, KM, PRECISE, NC>;                                          \
     if (smem > 48 * 1024) VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<a.B, kAttnThreads, smem, stream>>>(a);                                                        \
   } while (0)
-  if (a.K == 1) VC_ATTN_LAUNCH(1);
-  else if (a.K <= 3) VC_ATTN_LAUNCH(3);
-  else if (a.K <= 5) VC_ATTN_LAUNCH(5);
-  else if (a.K <= 8) VC_ATTN_LAUNCH(8);
-  else VC_ATTN_LAUNCH(16);
+  constexpr bool kPacked = (MODE == ATTN_ADDITIVE) && std::is_same<KT, __half>::value;
+  bool done = false;
+  if constexpr (kPacked) {
+    // register-resident queries: exact K in {1,3,5}, D <= 512
+    if (a.D <= 256) {
+      if (a.K == 1) { VC_ATTN_LAUNCH(1, 1); done = true; }
+      else if (a.K == 3) { VC_ATTN_LAUNCH(3, 1); done = true; }
+      else if (a.K == 5) { VC_ATTN_LAUNCH(5, 1); done = true; }
+    } else if (a.D <= 512) {
+      if (a.K == 1) { VC_ATTN_LAUNCH(1, 2); done = true; }
+      else if (a.K == 3) { VC_ATTN_LAUNCH(3, 2); done = true; }
+      else if (a.K == 5) { VC_ATTN_LAUNCH(5, 2); done = true; }
+    }
+  }
+  if (!done) {
+    if (a.K == 1) VC_ATTN_LAUNCH(1, 0);
+    else if (a.K <= 3) VC_ATTN_LAUNCH(3, 0);
+    else if (a.K <= 5) VC_ATTN_LAUNCH(5, 0);
+    else if (a.K <= 8) VC_ATTN_LAUNCH(8, 0);
+    else VC_ATTN_LAUNCH(16, 0);
+  }
 #undef VC_ATTN_LAUNCH
   VC_CUDA(cudaGetLastError());
   return VC_OK;

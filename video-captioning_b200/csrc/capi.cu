@@ -513,7 +513,11 @@ int run_precompute(vc_model* m, WS<ActT>& w, int B, int T, cudaStream_t s) {
   const int H = d.hidden_dim, A = d.attn_dim, BT = B * T;
   VC_SCOPE(VC_CLS_ATTN_PRECOMPUTE);
   if (d.attention == VC_ATTN_BAHDANAU || d.attention == VC_ATTN_LUONG_CONCAT) {
-    VC_TRY((gemm<ActT>(gargs(w.enc_act, H, m->Wkey, H, BT, A, H), H, estore<ActT, false, P>(w.keys, A, m->bkey), s)));
+    // bf16 mode stores the additive keys as fp16 (same footprint, 3 more mantissa bits) for the packed
+    // half2 add/tanh/fma of the attention step
+    using KeyT = typename std::conditional<P, float, __half>::type;
+    VC_TRY((gemm<ActT>(gargs(w.enc_act, H, m->Wkey, H, BT, A, H), H,
+                       estore<KeyT, false, P>(reinterpret_cast<KeyT*>(w.keys), A, m->bkey), s)));
   } else if (d.attention == VC_ATTN_MULTIHEAD) {
     VC_TRY((gemm<ActT>(gargs(w.enc_act, H, m->Wkey, H, BT, H, H), H, estore<ActT, false, P>(w.keys, H, m->bkey), s)));
     VC_TRY((gemm<ActT>(gargs(w.enc_act, H, m->Wval, H, BT, H, H), H, estore<ActT, false, P>(w.vals, H, m->bval), s)));
@@ -542,12 +546,13 @@ int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64
       }
       a.skeys = w.keys; a.q = w.Q; a.v = m->vvec; a.v_bias = m->vbias; a.D = A;
       VC_SCOPE(VC_CLS_ATTN_STEP);
-      return launch_attn_step<ActT, ATTN_ADDITIVE, P>(a, s);
+      using KeyT = typename std::conditional<P, float, __half>::type;
+      return launch_attn_step<ActT, KeyT, ATTN_ADDITIVE, P>(a, s);
     }
     case VC_ATTN_LUONG_DOT: {
       a.skeys = w.enc_act; a.q_act = hq; a.q_ld = hq_ld; a.D = H;
       VC_SCOPE(VC_CLS_ATTN_STEP);
-      return launch_attn_step<ActT, ATTN_DOT, P>(a, s);
+      return launch_attn_step<ActT, ActT, ATTN_DOT, P>(a, s);
     }
     case VC_ATTN_LUONG_GENERAL: {
       {
@@ -556,7 +561,7 @@ int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64
       }
       a.skeys = w.enc_act; a.q = w.Q; a.D = H;
       VC_SCOPE(VC_CLS_ATTN_STEP);
-      return launch_attn_step<ActT, ATTN_DOT, P>(a, s);
+      return launch_attn_step<ActT, ActT, ATTN_DOT, P>(a, s);
     }
     case VC_ATTN_MULTIHEAD: {
       {
@@ -568,7 +573,7 @@ int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64
       a.ctx = w.ctx_pre; a.ctx_ld = H;
       {
         VC_SCOPE(VC_CLS_ATTN_STEP);
-        VC_TRY((launch_attn_step<ActT, ATTN_MHA, P>(a, s)));
+        VC_TRY((launch_attn_step<ActT, ActT, ATTN_MHA, P>(a, s)));
       }
       GemmArgs g = gargs(w.ctx_pre, H, m->Wao, H, R, H, H);
       EpiStore<ActT, false, P> e = estore<ActT, false, P>(ctx, ctx_ld, m->bao);                                          // :270
@@ -670,10 +675,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
                                              tokens_out, S, step);
     } else if (mode == DM_BEAM) {
       vc::LaunchScope _sel(VC_CLS_SELECT, s, 2);
-      if (K <= 3) beam_row_topk_kernel<3, P><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
-      else if (K <= 5) beam_row_topk_kernel<5, P><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
-      else if (K <= 8) beam_row_topk_kernel<8, P><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
-      else beam_row_topk_kernel<16, P><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
+      beam_row_topk_kernel<P><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
       beam_select_kernel<<<(B + 63) / 64, 64, 0, s>>>(bs, w.cand_val, w.cand_idx, B, K, V, S, step, p.end_token_id,
                                                       p.length_penalty, w.parent, w.cur_tok);
       parent = w.parent;
@@ -966,10 +968,7 @@ int vc_beam_select(const float* logits, const float* scores, int32_t B, int32_t 
   VC_CUDA(cudaMemcpyAsync(bs.scores, scores, sizeof(float) * R, cudaMemcpyDeviceToDevice, s));
   VC_CUDA(cudaMemsetAsync(bs.alive, 1, R, s));
   VC_CUDA(cudaMemsetAsync(bs.best_len, 0, sizeof(int) * B, s));
-  if (K <= 3) beam_row_topk_kernel<3, true><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
-  else if (K <= 5) beam_row_topk_kernel<5, true><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
-  else if (K <= 8) beam_row_topk_kernel<8, true><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
-  else beam_row_topk_kernel<16, true><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
+  beam_row_topk_kernel<true><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
   beam_select_kernel<<<(B + 63) / 64, 64, 0, s>>>(bs, cand_val, cand_idx, B, K, V, 1, 0, /*end_id=*/-1, 1.0f, parent, token);
   VC_CUDA(cudaGetLastError());
   VC_CUDA(cudaMemcpyAsync(new_scores, bs.scores, sizeof(float) * R, cudaMemcpyDeviceToDevice, s));

@@ -1,6 +1,7 @@
 // Common device/host helpers for the B200 caption-generation kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -44,6 +45,8 @@ __device__ __forceinline__ float to_float(bf16 x) { return __bfloat162float(x); 
 template <class T> __device__ __forceinline__ T from_float(float x);
 template <> __device__ __forceinline__ float from_float<float>(float x) { return x; }
 template <> __device__ __forceinline__ bf16 from_float<bf16>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ __half from_float<__half>(float x) { return __float2half_rn(x); }
+__device__ __forceinline__ float to_float(__half x) { return __half2float(x); }
 
 // Load 4 consecutive elements as floats (pointer 16B- (float) / 8B- (bf16) aligned).
 __device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
@@ -67,6 +70,14 @@ __device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
   t.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p) = t;
 }
+__device__ __forceinline__ void store4(__half* p, const float (&v)[4]) {
+  __half2 a = __floats2half2_rn(v[0], v[1]);
+  __half2 b = __floats2half2_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
 // 8 consecutive elements (32B float / 16B bf16 aligned)
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   float4 a = *reinterpret_cast<const float4*>(p);
@@ -78,6 +89,13 @@ __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
   for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  uint4 t = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
 
 // Precise and fast transcendental flavours.  PRECISE is used by the fp32 parity mode (bit-level

@@ -101,111 +101,214 @@ __global__ void __launch_bounds__(256) greedy_argmax_kernel(const float* __restr
 // ---------------------------------------------------------------- beam: per-row log-softmax stats + top-K
 // (video_captioning_model.py:209 log_softmax, first half of :215 topk).  The top-K over the K*V
 // candidates of a video is contained in the union of the per-row top-K, so each row only exports its K
-// best log-probs.  One CTA per row, one pass over the logits (HBM-bound: R*V*4 bytes per step):
-// per-thread online (max, sum-exp) + sorted K-list, then shuffle-only merges (lanes -> warp -> CTA).
-// Order everywhere: value desc, vocabulary index asc (ties resolve to the lower index).
-template <int KMAX>
-struct TopList {
-  float v[KMAX];
-  int i[KMAX];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) { v[k] = -INFINITY; i[k] = 0x7fffffff; }
+// best log-probs.  One CTA per row, one pass over the logits (HBM-bound: R*V*4 bytes per step).
+//
+// SIMT-friendly selection: every warp keeps ONE sorted K-list distributed over its lanes (lane j holds the
+// j-th best) plus the warp-uniform threshold (the K-th best).  Elements are compared against the threshold
+// only; the rare survivors (about K*ln(n/K) per warp) are found with a ballot and inserted one at a time
+// with a popc/shfl_up shift.  (Per-thread lists cost ~100 instructions per element: with 32 lanes some lane
+// inserts at almost every element.)  Order everywhere: value desc, vocabulary index asc.
+struct WarpTopK {
+  float lv; int li;        // lane j < K: j-th best so far
+  float thr; int thr_i;    // warp-uniform K-th best
+  int K, lane;
+  __device__ __forceinline__ void init(int K_, int lane_) {
+    K = K_; lane = lane_; lv = -INFINITY; li = 0x7fffffff; thr = -INFINITY; thr_i = 0x7fffffff;
   }
-  // insert (y, idx); caller guarantees y > v[KMAX-1] or (y == v[KMAX-1] && idx < i[KMAX-1])
+  __device__ __forceinline__ bool passes(float y, int idx) const { return y > thr || (y == thr && idx < thr_i); }
+  // warp-uniform candidate
   __device__ __forceinline__ void insert(float y, int idx) {
-    v[KMAX - 1] = y; i[KMAX - 1] = idx;
-#pragma unroll
-    for (int k = KMAX - 1; k > 0; --k) {
-      const bool up = v[k] > v[k - 1] || (v[k] == v[k - 1] && i[k] < i[k - 1]);
-      if (up) {
-        const float a = v[k]; v[k] = v[k - 1]; v[k - 1] = a;
-        const int c = i[k]; i[k] = i[k - 1]; i[k - 1] = c;
-      }
-    }
+    const bool better = (lane < K) && (lv > y || (lv == y && li < idx));
+    const int p = __popc(__ballot_sync(0xffffffffu, better));   // sorted list: the better entries are lanes 0..p-1
+    if (p >= K) return;
+    const float uv = __shfl_up_sync(0xffffffffu, lv, 1);
+    const int ui = __shfl_up_sync(0xffffffffu, li, 1);
+    if (lane == p) { lv = y; li = idx; }
+    else if (lane > p && lane < K) { lv = uv; li = ui; }
+    // the threshold only ever rises (it may have been seeded above the still-unfilled list tail)
+    const float nt = __shfl_sync(0xffffffffu, lv, K - 1);
+    const int ni = __shfl_sync(0xffffffffu, li, K - 1);
+    if (nt >= thr) { thr = nt; thr_i = ni; }
   }
-  __device__ __forceinline__ void pop() {
-#pragma unroll
-    for (int k = 0; k < KMAX - 1; ++k) { v[k] = v[k + 1]; i[k] = i[k + 1]; }
-    v[KMAX - 1] = -INFINITY; i[KMAX - 1] = 0x7fffffff;
+  // Seed the threshold with a lower bound of the K-th best: the K-th largest of the lanes' values `x`
+  // (ties removed together, which only lowers the bound).  Equal elements still pass (thr_i = INT_MAX).
+  __device__ __forceinline__ void seed(float x) {
+    float bound = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      bound = warp_max(x);
+      if (x == bound) x = -INFINITY;
+    }
+    if (bound > thr) { thr = bound; thr_i = 0x7fffffff; }
+  }
+  // each lane offers one (y, idx); survivors are inserted in lane order
+  __device__ __forceinline__ void offer(float y, int idx) {
+    unsigned mask = __ballot_sync(0xffffffffu, passes(y, idx));
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float cy = __shfl_sync(0xffffffffu, y, src);
+      const int ci = __shfl_sync(0xffffffffu, idx, src);
+      if (passes(cy, ci)) insert(cy, ci);
+    }
   }
 };
 
-// K rounds of warp arg-max over the lanes' list heads; lane `k` ends up holding the k-th best of the warp.
-template <int KMAX>
-__device__ __forceinline__ void warp_merge_topk(TopList<KMAX>& l, int K, int lane, float& out_v, int& out_i) {
-  out_v = -INFINITY; out_i = 0x7fffffff;
-  for (int k = 0; k < K; ++k) {
-    float bv = l.v[0];
-    int bi = l.i[0];
+// Streaming selection without warp collectives in the hot loop:
+//   phase 1  the first 4096 columns are streamed for the log-sum-exp only, each thread keeping the maximum
+//            of its 16 values; the K-th largest of the 256 thread maxima is a LOWER BOUND of the K-th best
+//            logit of the row (about the 5th best of 4096 -> ~12 of the 10k columns exceed it);
+//   phase 2  the remaining columns are streamed with log-sum-exp + one compare per float4; the rare survivors
+//            are appended to a shared-memory buffer with a single hand-rolled atomic per thread;
+//   phase 3  the first 4096 columns are re-scanned (L1/L2 hits) with the compare only;
+//   phase 4  warp 0 picks the exact top-K of the survivors (value desc, index asc).
+// If the buffer overflows (e.g. thousands of equal logits) warp 0 falls back to the exact streaming
+// selection above.  The row is read from HBM exactly once.
+__device__ __forceinline__ void topk_append(float (&y)[4], int i, float thr, int* cnt, float* bv, int* bi, int cap) {
+  int c = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  for (int j = 0; j < 4; ++j) c += (y[j] >= thr) ? 1 : 0;
+  int p;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(p) : "r"((uint32_t)__cvta_generic_to_shared(cnt)), "r"(c) : "memory");
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (y[j] >= thr) {
+      if (p < cap) { bv[p] = y[j]; bi[p] = i + j; }
+      ++p;
     }
-    if (l.i[0] == bi && l.v[0] == bv) l.pop();     // indices are unique within a row: exactly one lane pops
-    if (lane == k) { out_v = bv; out_i = bi; }
-  }
 }
 
-template <int KMAX, bool PRECISE>
+template <bool PRECISE>
 __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restrict__ logits, int64_t ld, int V, int K,
                                                             float* __restrict__ cand_val /*[R,K] log-prob*/,
                                                             int* __restrict__ cand_idx /*[R,K]*/) {
+  constexpr int CAP = 1024, nwarp = 8, kSampleIters = 4;
+  __shared__ float bv[CAP];
+  __shared__ int bi[CAP];
+  __shared__ int cnt;
+  __shared__ float s_top[nwarp][16], sm[nwarp], ss[nwarp];
   const int r = blockIdx.x;
   const float* row = logits + (int64_t)r * ld;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int nwarp = 8;
-  TopList<KMAX> tl;
-  tl.init();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sample_end = min(V, kSampleIters * 1024);
+
+  // ---- phase 1: sample (log-sum-exp + thread maximum)
   float m = -INFINITY, s = 0.f;
-  for (int i = threadIdx.x * 4; i < V; i += 256 * 4) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(row + i));
-    const float v[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float y = v[j];
-      if (y > m) {
-        s *= PRECISE ? expf(m - y) : __expf(m - y);
-        m = y;
-      }
-      s += PRECISE ? expf(y - m) : __expf(y - m);
-      if (y > tl.v[KMAX - 1]) tl.insert(y, i + j);   // strictly greater: the earlier index keeps ties
+  for (int i = tid * 4; i < sample_end; i += 1024) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(row + i));
+    const float m4 = fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w));
+    if (m4 > m) {
+      s *= PRECISE ? expf(m - m4) : __expf(m - m4);
+      m = m4;
+    }
+    s += PRECISE ? (expf(t.x - m) + expf(t.y - m)) + (expf(t.z - m) + expf(t.w - m))
+                 : (__expf(t.x - m) + __expf(t.y - m)) + (__expf(t.z - m) + __expf(t.w - m));
+  }
+  {
+    // K largest (distinct) thread maxima of this warp -> smem; uniform control flow
+    float x = m;
+    for (int k = 0; k < K; ++k) {
+      const float b = warp_max(x);
+      if (x == b) x = -INFINITY;
+      if (lane == 0) s_top[warp][k] = b;
+    }
+    if (tid == 0) cnt = 0;
+  }
+  __syncthreads();
+  float thr;
+  {
+    // K-th largest of the nwarp*K collected values (every warp computes it redundantly: no second barrier)
+    float a = -INFINITY, b2 = -INFINITY;          // two candidates per lane cover up to 64 >= nwarp*K... K <= 8 here
+    const int total = nwarp * K;
+    if (lane < total) a = s_top[lane / K][lane % K];
+    if (lane + 32 < total) b2 = s_top[(lane + 32) / K][(lane + 32) % K];
+    if (lane + 64 < total) b2 = fmaxf(b2, s_top[(lane + 64) / K][(lane + 64) % K]);   // K > 8: looser (still valid) bound
+    if (lane + 96 < total) b2 = fmaxf(b2, s_top[(lane + 96) / K][(lane + 96) % K]);
+    thr = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      const float x = fmaxf(a, b2);
+      thr = warp_max(x);
+      if (a == thr) a = -INFINITY;
+      else if (b2 == thr) b2 = -INFINITY;
     }
   }
-  // log-sum-exp of the row
-  __shared__ float sm[nwarp], ss[nwarp], wv[nwarp][KMAX];
-  __shared__ int wi[nwarp][KMAX];
+
+  // ---- phase 2: the rest of the row
+  for (int i = sample_end + tid * 4; i < V; i += 1024) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(row + i));
+    float y[4] = {t.x, t.y, t.z, t.w};
+    const float m4 = fmaxf(fmaxf(y[0], y[1]), fmaxf(y[2], y[3]));
+    if (m4 > m) {
+      s *= PRECISE ? expf(m - m4) : __expf(m - m4);
+      m = m4;
+    }
+    s += PRECISE ? (expf(y[0] - m) + expf(y[1] - m)) + (expf(y[2] - m) + expf(y[3] - m))
+                 : (__expf(y[0] - m) + __expf(y[1] - m)) + (__expf(y[2] - m) + __expf(y[3] - m));
+    if (m4 >= thr) topk_append(y, i, thr, &cnt, bv, bi, CAP);
+  }
+  // ---- phase 3: survivors of the sample (cache hits)
+  for (int i = tid * 4; i < sample_end; i += 1024) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(row + i));
+    float y[4] = {t.x, t.y, t.z, t.w};
+    if (fmaxf(fmaxf(y[0], y[1]), fmaxf(y[2], y[3])) >= thr) topk_append(y, i, thr, &cnt, bv, bi, CAP);
+  }
   const float wm = warp_max(m);
   const float wsum = warp_sum(m == -INFINITY ? 0.f : s * (PRECISE ? expf(m - wm) : __expf(m - wm)));
-  float ov;
-  int oi;
-  warp_merge_topk<KMAX>(tl, K, lane, ov, oi);
   if (lane == 0) { sm[warp] = wm; ss[warp] = wsum; }
-  if (lane < K) { wv[warp][lane] = ov; wi[warp][lane] = oi; }
   __syncthreads();
-  if (warp == 0) {
-    float M = sm[0];
+  if (warp != 0) return;
+
+  // ---- phase 4
+  float M = sm[0];
 #pragma unroll
-    for (int w = 1; w < nwarp; ++w) M = fmaxf(M, sm[w]);
-    float S = 0.f;
+  for (int w = 1; w < nwarp; ++w) M = fmaxf(M, sm[w]);
+  float S = 0.f;
 #pragma unroll
-    for (int w = 0; w < nwarp; ++w) S += ss[w] * (PRECISE ? expf(sm[w] - M) : __expf(sm[w] - M));
-    const float lse = M + logf(S);
-    // lanes 0..7 adopt warp w's (already sorted) K-list and the 8 lists are merged the same way
-    TopList<KMAX> t2;
-    t2.init();
-    if (lane < nwarp) {
+  for (int w = 0; w < nwarp; ++w) S += (sm[w] == -INFINITY) ? 0.f : ss[w] * (PRECISE ? expf(sm[w] - M) : __expf(sm[w] - M));
+  const float lse = M + logf(S);
+  const int n = cnt;
+  float ov = -INFINITY;
+  int oi = 0x7fffffff;
+  if (n <= CAP) {
+    // exact top-K of the n survivors: K rounds of (lane-local best, warp arg-max, remove)
+    for (int k = 0; k < K; ++k) {
+      float lbv = -INFINITY;
+      int lbi = 0x7fffffff, lpos = -1;
+      for (int p = lane; p < n; p += 32) {
+        const float v = bv[p];
+        const int ix = bi[p];
+        if (v > lbv || (v == lbv && ix < lbi)) { lbv = v; lbi = ix; lpos = p; }
+      }
+      float wv = lbv;
+      int wi = lbi;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < K) { t2.v[k] = wv[lane][k]; t2.i[k] = wi[lane][k]; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float tv = __shfl_xor_sync(0xffffffffu, wv, o);
+        const int ti = __shfl_xor_sync(0xffffffffu, wi, o);
+        if (tv > wv || (tv == wv && ti < wi)) { wv = tv; wi = ti; }
+      }
+      if (lpos >= 0 && lbi == wi && lbv == wv) { bv[lpos] = -INFINITY; bi[lpos] = 0x7fffffff; }   // unique index: one lane
+      __syncwarp();
+      if (lane == k) { ov = wv; oi = wi; }
     }
-    warp_merge_topk<KMAX>(t2, K, lane, ov, oi);
-    if (lane < K) {
-      cand_val[(int64_t)r * K + lane] = ov - lse;    // log_softmax value of the k-th best token
-      cand_idx[(int64_t)r * K + lane] = oi;
+  } else {
+    WarpTopK tk;
+    tk.init(K, lane);
+    for (int base = 0; base < V; base += 128) {
+      const int i = base + lane * 4;
+      float y[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (i < V) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(row + i));
+        y[0] = t.x; y[1] = t.y; y[2] = t.z; y[3] = t.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tk.offer(y[j], i < V ? i + j : 0x7fffffff);
     }
+    ov = tk.lv;
+    oi = tk.li;
+  }
+  if (lane < K) {
+    cand_val[(int64_t)r * K + lane] = ov - lse;    // log_softmax value of the k-th best token
+    cand_idx[(int64_t)r * K + lane] = oi;
   }
 }
 

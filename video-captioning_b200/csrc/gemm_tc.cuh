@@ -139,6 +139,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+template <class OutT> __device__ __forceinline__ uint32_t pack16(float lo, float hi) { return pack_bf16(lo, hi); }
+template <> __device__ __forceinline__ uint32_t pack16<__half>(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
@@ -300,8 +305,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs g) {
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              sts128(swz(box, r, h * 4 + j), pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                     pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+              sts128(swz(box, r, h * 4 + j), pack16<OutT>(f[8 * j], f[8 * j + 1]), pack16<OutT>(f[8 * j + 2], f[8 * j + 3]),
+                     pack16<OutT>(f[8 * j + 4], f[8 * j + 5]), pack16<OutT>(f[8 * j + 6], f[8 * j + 7]));
           }
         }
         fence_proxy_async_smem();
