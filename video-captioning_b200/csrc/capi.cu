@@ -676,7 +676,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
     } else if (mode == DM_BEAM) {
       vc::LaunchScope _sel(VC_CLS_SELECT, s, 2);
       beam_row_topk_kernel<P><<<R, 256, 0, s>>>(lg, ldl, V, K, w.cand_val, w.cand_idx);
-      beam_select_kernel<<<(B + 63) / 64, 64, 0, s>>>(bs, w.cand_val, w.cand_idx, B, K, V, S, step, p.end_token_id,
+      beam_select_kernel<<<(B + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, s>>>(bs, w.cand_val, w.cand_idx, B, K, V, S, step, p.end_token_id,
                                                       p.length_penalty, w.parent, w.cur_tok);
       parent = w.parent;
     } else if (step + 1 < S) {
@@ -969,7 +969,7 @@ int vc_beam_select(const float* logits, const float* scores, int32_t B, int32_t 
   VC_CUDA(cudaMemsetAsync(bs.alive, 1, R, s));
   VC_CUDA(cudaMemsetAsync(bs.best_len, 0, sizeof(int) * B, s));
   beam_row_topk_kernel<true><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
-  beam_select_kernel<<<(B + 63) / 64, 64, 0, s>>>(bs, cand_val, cand_idx, B, K, V, 1, 0, /*end_id=*/-1, 1.0f, parent, token);
+  beam_select_kernel<<<(B + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, s>>>(bs, cand_val, cand_idx, B, K, V, 1, 0, /*end_id=*/-1, 1.0f, parent, token);
   VC_CUDA(cudaGetLastError());
   VC_CUDA(cudaMemcpyAsync(new_scores, bs.scores, sizeof(float) * R, cudaMemcpyDeviceToDevice, s));
   return VC_OK;

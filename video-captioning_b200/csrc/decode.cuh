@@ -331,77 +331,110 @@ struct BeamState {
   int* hist[2];             // [R,S] token history, ping-pong
 };
 
-__global__ void beam_select_kernel(BeamState bs, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
-                                   int B, int K, int V, int S, int step, int end_id, float length_penalty,
-                                   int* __restrict__ parent /*[R]*/, int* __restrict__ cur_tok /*[R]*/) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+constexpr int kSelWarps = 4;   // videos per CTA (one warp each)
+
+__global__ void __launch_bounds__(kSelWarps * 32) beam_select_kernel(
+    BeamState bs, const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int B, int K, int V, int S, int step,
+    int end_id, float length_penalty, int* __restrict__ parent /*[R]*/, int* __restrict__ cur_tok /*[R]*/) {
+  __shared__ float s_v[kSelWarps][16], s_ns[kSelWarps][16];
+  __shared__ int s_pk[kSelWarps][16], s_nt[kSelWarps][16];    // selection order: parent beam, token
+  __shared__ int s_np[kSelWarps][16], s_tk[kSelWarps][16];    // compacted live beams: parent beam, token
+  __shared__ int s_misc[kSelWarps][4];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * kSelWarps + w;
+  if (b >= B) return;                       // warp-uniform
   const int* hin = bs.hist[step & 1];
   int* hout = bs.hist[(step + 1) & 1];
-  const int r0 = b * K;
-  unsigned used[8];   // bitset over K*K <= 256 candidates
-  for (int i = 0; i < 8; ++i) used[i] = 0u;
-  int n_alive = 0;
-  float new_score[16];
-  int new_parent[16], new_tok[16];
-  const int n_live_in = [&] { int c = 0; for (int k = 0; k < K; ++k) c += bs.alive[r0 + k] ? 1 : 0; return c; }();
-  if (n_live_in > 0) {
-    for (int sel = 0; sel < K; ++sel) {
-      float bv = -INFINITY;
-      long long bflat = 0x7fffffffffffffffLL;
-      int bc = -1;
-      for (int k = 0; k < K; ++k) {
-        if (!bs.alive[r0 + k]) continue;
-        const float base = bs.scores[r0 + k];
-        for (int j = 0; j < K; ++j) {
-          const int c = k * K + j;
-          if (used[c >> 5] & (1u << (c & 31))) continue;
-          const float v = base + cand_val[(int64_t)(r0 + k) * K + j];
-          const long long flat = (long long)k * V + cand_idx[(int64_t)(r0 + k) * K + j];
-          if (v > bv || (v == bv && flat < bflat) || bc < 0) { bv = v; bflat = flat; bc = c; }
-        }
+  const int r0 = b * K, KK = K * K;
+
+  // candidates c = k*K + j (beam k, its j-th best token): lane owns c = lane + 32*q
+  float cv[8];
+  int cf[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = lane + 32 * q;
+    cv[q] = -INFINITY;
+    cf[q] = 0x7fffffff;
+    if (c < KK) {
+      const int k = c / K;
+      if (bs.alive[r0 + k]) {
+        cv[q] = bs.scores[r0 + k] + cand_val[(int64_t)(r0 + k) * K + (c - k * K)];       // :211
+        cf[q] = k * V + cand_idx[(int64_t)(r0 + k) * K + (c - k * K)];                   // flat index of :215
       }
-      if (bc < 0) break;
-      used[bc >> 5] |= 1u << (bc & 31);
-      const int pk = bc / K;
-      const int tok = cand_idx[(int64_t)(r0 + pk) * K + (bc - pk * K)];
+    }
+  }
+  // top-K by (score desc, flat asc): K rounds of warp arg-max  (:215-220)
+  int n_sel = 0;
+  for (int sel = 0; sel < K; ++sel) {
+    float bv = -INFINITY;
+    int bf = 0x7fffffff, bq = -1;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (cf[q] != 0x7fffffff && (bq < 0 || cv[q] > bv || (cv[q] == bv && cf[q] < bf))) { bv = cv[q]; bf = cf[q]; bq = q; }
+    float wv = bv;
+    int wf = bf;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float tv = __shfl_xor_sync(0xffffffffu, wv, o);
+      const int tf = __shfl_xor_sync(0xffffffffu, wf, o);
+      if (tf != 0x7fffffff && (wf == 0x7fffffff || tv > wv || (tv == wv && tf < wf))) { wv = tv; wf = tf; }
+    }
+    if (wf == 0x7fffffff) break;            // no live candidate left (warp-uniform)
+    if (bq >= 0 && bf == wf) {              // flat indices are unique: exactly one owner
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q == bq) cf[q] = 0x7fffffff;
+      s_v[w][sel] = wv;
+      s_pk[w][sel] = wf / V;                // :219
+      s_nt[w][sel] = wf % V;                // :220
+    }
+    ++n_sel;
+  }
+  __syncwarp();
+  // END bookkeeping + compaction of the live beams (:226-272), sequential in selection order
+  if (lane == 0) {
+    int n_alive = 0, best_pk = -1, best_tok = 0;
+    float best_score = bs.best_score[b];
+    int best_len = bs.best_len[b];
+    for (int sel = 0; sel < n_sel; ++sel) {
+      const int pk = s_pk[w][sel], tok = s_nt[w][sel];
+      const float v = s_v[w][sel];
       if (tok == end_id) {
-        const float denom = (float)pow((double)(step + 1), (double)length_penalty);   // (len(new_seq)-1)**lp
-        const float fin = bv / denom;
-        if (bs.best_len[b] == 0 || fin > bs.best_score[b]) {
-          bs.best_score[b] = fin;
-          bs.best_len[b] = step + 1;
-          for (int i = 0; i < step; ++i) bs.best_seq[(int64_t)b * S + i] = hin[(int64_t)(r0 + pk) * S + i];
-          bs.best_seq[(int64_t)b * S + step] = tok;
-        }
+        const float fin = v / (float)pow((double)(step + 1), (double)length_penalty);   // (len(new_seq)-1)**lp, :238-239
+        if (best_len == 0 || fin > best_score) { best_score = fin; best_len = step + 1; best_pk = pk; best_tok = tok; }
       } else {
-        new_score[n_alive] = bv;
-        new_parent[n_alive] = pk;
-        new_tok[n_alive] = tok;
+        s_np[w][n_alive] = pk;
+        s_ns[w][n_alive] = v;
+        s_tk[w][n_alive] = tok;
         ++n_alive;
       }
     }
+    if (best_pk >= 0) { bs.best_score[b] = best_score; bs.best_len[b] = best_len; }
+    s_misc[w][0] = n_alive;
+    s_misc[w][1] = best_pk;
+    s_misc[w][2] = best_tok;
+    if (n_alive == 0) bs.done[b] = 1;       // :251
+  }
+  __syncwarp();
+  const int n_alive = s_misc[w][0], best_pk = s_misc[w][1];
+  if (best_pk >= 0) {
+    for (int i = lane; i < step; i += 32) bs.best_seq[(int64_t)b * S + i] = hin[(int64_t)(r0 + best_pk) * S + i];
+    if (lane == 0) bs.best_seq[(int64_t)b * S + step] = s_misc[w][2];
   }
   for (int k = 0; k < K; ++k) {
     const int r = r0 + k;
-    if (k < n_alive) {
-      bs.scores[r] = new_score[k];
-      bs.alive[r] = 1;
-      parent[r] = r0 + new_parent[k];
-      cur_tok[r] = new_tok[k];
-      for (int i = 0; i < step; ++i) hout[(int64_t)r * S + i] = hin[(int64_t)(r0 + new_parent[k]) * S + i];
-      hout[(int64_t)r * S + step] = new_tok[k];
-    } else {
-      // dead slot: keeps computing on benign inputs, never contributes candidates
-      bs.alive[r] = 0;
-      bs.scores[r] = -INFINITY;
-      parent[r] = r;
-      cur_tok[r] = end_id;
-      for (int i = 0; i < step; ++i) hout[(int64_t)r * S + i] = hin[(int64_t)r * S + i];
-      hout[(int64_t)r * S + step] = end_id;
+    const bool live = k < n_alive;
+    const int src = live ? r0 + s_np[w][k] : r;       // dead slot: keeps computing on benign inputs
+    const int tok = live ? s_tk[w][k] : end_id;
+    for (int i = lane; i < step; i += 32) hout[(int64_t)r * S + i] = hin[(int64_t)src * S + i];
+    if (lane == 0) {
+      hout[(int64_t)r * S + step] = tok;
+      bs.scores[r] = live ? s_ns[w][k] : -INFINITY;
+      bs.alive[r] = live ? 1 : 0;
+      parent[r] = src;
+      cur_tok[r] = tok;
     }
   }
-  if (n_alive == 0) bs.done[b] = 1;
 }
 
 // ---------------------------------------------------------------- reorder (+ next-step embedding)

@@ -79,6 +79,10 @@ class VideoCaptioningModel(nn.Module):
         self.feature_extractor = None     # CNN extractors are out of scope (precomputed features)
         self.precision = precision
         self.chunk_size = int(chunk_size)  # videos per native call (bounds the workspace)
+        self.host_chunk_size = 256         # videos per H2D chunk when the features live in host memory
+        self._copy_stream = None
+        self._staging = None
+        self._staging_key = None
         self._native_key = None
         self._native_handle: Optional[_native.NativeModel] = None
         self.encoder._owner = weakref.ref(self)
@@ -129,13 +133,16 @@ class VideoCaptioningModel(nn.Module):
             raise TypeError(f"generate(method='{method}') got unexpected keyword arguments {sorted(bad)}")
         h = self._handle()
         B = video_features.shape[0]
-        outs = []
-        for lo in range(0, B, self.chunk_size):
-            hi = min(B, lo + self.chunk_size)
-            mk = None if video_mask is None else video_mask[lo:hi]
-            outs.append(h.generate(video_features[lo:hi], start_token_id, end_token_id, max_length, mk, method,
-                                   beam_size=kwargs.get("beam_size", 5), length_penalty=kwargs.get("length_penalty", 1.0),
-                                   temperature=kwargs.get("temperature", 1.0), diverse=kwargs.get("diverse_beams", False)))
+        gen = lambda x, mk: h.generate(x, start_token_id, end_token_id, max_length, mk, method,
+                                       beam_size=kwargs.get("beam_size", 5), length_penalty=kwargs.get("length_penalty", 1.0),
+                                       temperature=kwargs.get("temperature", 1.0), diverse=kwargs.get("diverse_beams", False))
+        if video_features.device.type == "cpu":
+            outs = self._generate_from_host(h, video_features, video_mask, gen)
+        else:
+            outs = []
+            for lo in range(0, B, self.chunk_size):
+                hi = min(B, lo + self.chunk_size)
+                outs.append(gen(video_features[lo:hi], None if video_mask is None else video_mask[lo:hi]))
         tokens = torch.cat([o[0] for o in outs], dim=0)
         if method == "greedy":
             attn = torch.cat([o[3] for o in outs], dim=0)
@@ -148,6 +155,48 @@ class VideoCaptioningModel(nn.Module):
         scores = torch.cat([o[2] for o in outs], dim=0)
         L = int(lens.max())
         return {"generated_tokens": tokens[:, :L].to(torch.int64), "lengths": lens.to(torch.int64), "scores": scores}
+
+    def _generate_from_host(self, h, feats: torch.Tensor, mask, gen):
+        """Feature ingest for HOST tensors (predictor.py:101-107 does one blocking H2D per video): the batch is
+        streamed to the device in chunks on a copy stream, double-buffered, so the PCIe transfer of chunk
+        i+1 overlaps the compute of chunk i.  Pass pinned memory (``tensor.pin_memory()``) for full speed.
+        The arithmetic still runs only on the GPU."""
+        if feats.dtype != torch.float32 or feats.dim() != 3:
+            raise ValueError("host video_features must be a float32 [B,T,F] tensor")
+        dev = h.device
+        B, T, F = feats.shape
+        chunk = max(1, min(self.host_chunk_size, self.chunk_size, B))
+        compute = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        key = (chunk, T, F, str(dev))
+        if self._staging_key != key:
+            self._staging = [torch.empty(chunk, T, F, dtype=torch.float32, device=dev) for _ in range(2)]
+            self._staging_key = key
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        spans = [(lo, min(B, lo + chunk)) for lo in range(0, B, chunk)]
+
+        def enqueue_copy(i):
+            lo, hi = spans[i]
+            with torch.cuda.stream(self._copy_stream):
+                if i >= 2:
+                    self._copy_stream.wait_event(free[i % 2])
+                else:
+                    self._copy_stream.wait_stream(compute)      # earlier users of the staging buffers
+                self._staging[i % 2][: hi - lo].copy_(feats[lo:hi], non_blocking=True)
+                ready[i % 2].record(self._copy_stream)
+
+        outs = []
+        enqueue_copy(0)
+        for i, (lo, hi) in enumerate(spans):
+            if i + 1 < len(spans):
+                enqueue_copy(i + 1)
+            compute.wait_event(ready[i % 2])
+            mk = None if mask is None else mask[lo:hi].to(dev, non_blocking=True)
+            outs.append(gen(self._staging[i % 2][: hi - lo], mk))
+            free[i % 2].record(compute)
+        return outs
 
     def forward(self, video_features, input_tokens, target_tokens, video_mask=None) -> Dict[str, torch.Tensor]:
         """Teacher-forced forward, video_captioning_model.py:35-77 (inference only: no autograd graph)."""
