@@ -7,6 +7,7 @@
 // S decode steps (decoder.py:108-171) with greedy (decoder.py:223-289) or beam
 // (video_captioning_model.py:148-302) selection, all enqueued on one stream with no host sync.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -20,6 +21,7 @@
 #include "gemm_common.cuh"
 #include "gemm_f32.cuh"
 #include "gemm_tc.cuh"
+#include "lstm_persistent.cuh"
 
 namespace vc {
 
@@ -110,6 +112,8 @@ struct vc_model {
   std::map<std::string, std::pair<float*, int64_t>> raw;   // device fp32 copies of the reference state_dict
   std::vector<void*> owned;
   bool finalized = false;
+  int num_sms = 148;
+  bool disable_persistent_lstm = false;   // VC_DISABLE_PERSISTENT_LSTM=1: per-timestep launches (A/B testing)
   // derived, operand-typed (float or bf16 according to d.precision)
   void* Wp = nullptr; float* bp = nullptr;
   void* enc_Wih[4] = {}; float* enc_bias[4] = {};
@@ -309,6 +313,7 @@ template <class ActT>
 struct WS {
   bf16* feats_bf16;
   ActT *proj, *xp, *out[2], *zero_h, *hs[2], *enc_act, *keys, *vals;
+  unsigned int* flags;
   float *cst, *final_f32;
   ActT *Z, *XL[4], *Hn[4], *ctx_pre, *O;
   float *C[4], *Cn[4], *Q, *logits, *cand_val, *scores, *best_score;
@@ -333,6 +338,7 @@ WS<ActT> carve(const vc_model_desc_t& d, void* base, int B, int T, int K, int S)
   w.hs[0] = c.take<ActT>((size_t)B * 2 * H);
   w.hs[1] = c.take<ActT>((size_t)B * 2 * H);
   w.cst = c.take<float>((size_t)2 * B * H);
+  w.flags = c.take<unsigned int>(1024);
   w.enc_act = c.take<ActT>(BT * H);
   w.final_f32 = c.take<float>((size_t)B * H);
   if (d.attention == VC_ATTN_BAHDANAU || d.attention == VC_ATTN_LUONG_CONCAT) w.keys = c.take<ActT>(BT * A);
@@ -429,6 +435,21 @@ int run_encoder(vc_model* m, WS<ActT>& w, const float* feats, int B, int T, cons
                          estore<ActT, false, P>(w.xp, 8 * H, m->enc_bias[l]), s)));
     }
     out = w.out[l & 1];
+    if constexpr (!P) {
+      // bf16 mode: persistent weights-stationary kernel, one cooperative launch per (layer, batch chunk)
+      const int max_b = lengths ? 0 : tc::plstm_max_batch(H, m->num_sms);
+      if (max_b > 0 && !m->disable_persistent_lstm) {
+        for (int b0 = 0; b0 < B; b0 += max_b) {
+          const int bc = (B - b0 < max_b) ? (B - b0) : max_b;
+          VC_SCOPE(VC_CLS_ENC_RECURRENT);
+          VC_TRY(tc::launch_lstm_layer_persistent(out + (size_t)b0 * T * 2 * H, w.xp + (size_t)b0 * T * 8 * H,
+                                                  m->enc_Whh[l][0], m->enc_Whh[l][1], bc, T, H, w.flags, s));
+        }
+        layer_in = out;
+        in_dim = 2 * H;
+        continue;
+      }
+    }
     VC_CUDA(cudaMemsetAsync(w.cst, 0, sizeof(float) * (size_t)2 * B * H, s));
     if (lengths) VC_CUDA(cudaMemsetAsync(w.hs[0], 0, sizeof(ActT) * (size_t)B * 2 * H, s));
     for (int st = 0; st < T; ++st) {
@@ -779,6 +800,12 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   vc_model* m = new (std::nothrow) vc_model();
   VC_CHECK(m != nullptr, "out of host memory");
   m->d = d;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+    m->num_sms = sms;
+  cudaGetLastError();   // creating a handle must also work where no device is visible (CPU-side tests)
+  const char* env = getenv("VC_DISABLE_PERSISTENT_LSTM");
+  m->disable_persistent_lstm = env != nullptr && env[0] == '1';
   *out = m;
   return VC_OK;
 }

@@ -1,0 +1,329 @@
+// Persistent, weights-stationary bidirectional LSTM layer for sm_100a (bf16 mode).
+//
+// Replaces the 2*T dependent recurrent launches of one encoder layer (nn.LSTM inside encoder.py:84) with
+// ONE cooperative launch that runs all T timesteps of both directions:
+//
+//   grid  = (4H/128 gate-column tiles) x (ceil(B/256) row tiles) x (2 directions)   <= #SMs, 1 CTA / SM
+//   smem  = W_hh tile [128 x H] bf16, RESIDENT for the whole layer (128 KB at H=512)
+//           + 3-stage ring of h_{t-1} k-blocks (TMA), + the step's input-projection tile (TMA),
+//           + h staging boxes for the TMA stores
+//   TMEM  = two 128x128 fp32 accumulators (rows 0-127 / 128-255 of the CTA's row tile): the LSTM epilogue
+//           of one half overlaps the tcgen05 main loop of the other
+//   regs  = the cell state c (one row x 32 hidden units per epilogue thread) never leaves registers
+//
+// Per step each CTA computes gates[256 rows, 128 cols] = h_{t-1}[256, H] . W_tile^T + xproj_t + bias, applies
+// the fused cell (gate-interleaved columns: 32 hidden units per tile) and TMA-stores its h_t slice into the
+// layer output [B, T, 2H].  The 4H/128 CTAs that share a (direction, row-half) exchange h_t through L2:
+// a global arrival counter per group, released after the bulk store has completed and acquired by the TMA
+// producers before they load h_t for step t+1.  The spin is safe because the launch is cooperative
+// (all CTAs co-resident) and bounded (trap instead of hang).
+//
+// Warp roles (352 threads): w0 = h_{t-1} TMA producer, w1 = TMEM alloc + MMA issuer, w2-5 = epilogue of
+// row-half 0, w6-9 = epilogue of row-half 1, w10 = input-projection TMA producer.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "gemm_tc.cuh"
+
+namespace vc {
+namespace tc {
+
+constexpr int kPlThreads = 352;
+constexpr int kPlStages = 3;
+constexpr int kPlBN = 128;          // gate columns per CTA = 32 hidden units
+
+struct alignas(64) PLstmMaps {
+  CUtensorMap out_ld;   // layer output [B, T*2H] bf16, box 64 x 128, 128B swizzle (h_{t-1} loads)
+  CUtensorMap out_st;   // same buffer, box 32 x 128, 64B swizzle (h_t stores)
+  CUtensorMap W[2];     // W_hh [4H, H] per direction, box 64 x 128
+  CUtensorMap xp;       // input projections [B, T*8H] bf16, box 64 x 128
+};
+struct PLstmArgs {
+  int B, T, H;
+  const float* bias[2];      // nullable (the encoder's biases are folded into xp)
+  unsigned int* flags;       // [2 dirs][MT][2 halves] arrival counters, zeroed before launch
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// 16-byte chunk c (0..3) of row r in a 64-byte-row box with TMA SWIZZLE_64B (Swizzle<2,4,3>)
+__device__ __forceinline__ uint32_t swz64(uint32_t box, int r, int c) {
+  return box + (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(const __grid_constant__ PLstmMaps maps,
+                                                                             const PLstmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int H = g.H, T = g.T;
+  const int nkb = H / BK;
+  uint8_t* w_s = smem;                                    // nkb boxes of [128 n x 64 k] bf16
+  uint8_t* a_s = w_s + (size_t)nkb * kBoxBytes;           // kPlStages boxes of [128 rows x 64 k]
+  uint8_t* xp_s = a_s + (size_t)kPlStages * kBoxBytes;    // 2 boxes [128 rows x 64 cols] of one row-half
+  uint8_t* h_s = xp_s + 2 * kBoxBytes;                    // 2 x [128 rows x 32 units] bf16 (64B rows)
+  __shared__ __align__(8) uint64_t w_bar, full_bar[kPlStages], empty_bar[kPlStages];
+  // the input-projection buffer is shared by the two row-halves, but each half has its OWN full/empty
+  // barrier pair: with one shared pair a consumer can find the barrier two phases ahead (parity aliasing)
+  __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2], xp_full[2], xp_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float bias_s[kPlBN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.z;                               // direction
+  const int n0 = blockIdx.x * kPlBN;                      // gate column tile
+  const int m0 = blockIdx.y * 256;                        // row tile
+  const int NT = gridDim.x;
+  unsigned int* flag0 = g.flags + ((size_t)(z * gridDim.y + blockIdx.y) * 2);
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&w_bar), 1);
+    for (int s = 0; s < kPlStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(smem_u32(&tmem_full[h]), 1);
+      mbar_init(smem_u32(&tmem_empty[h]), 128);
+      mbar_init(smem_u32(&xp_full[h]), 1);
+      mbar_init(smem_u32(&xp_empty[h]), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < kPlBN) {
+    const float* bz = g.bias[z];
+    bias_s[threadIdx.x] = bz ? bz[n0 + threadIdx.x] : 0.f;
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== W_hh tile (once) + h_{t-1} k-blocks (every step) =====
+      mbar_expect_tx(smem_u32(&w_bar), (uint32_t)nkb * kBoxBytes);
+      for (int kb = 0; kb < nkb; ++kb)
+        tma_load_2d(smem_u32(w_s + (size_t)kb * kBoxBytes), &maps.W[z], smem_u32(&w_bar), kb * BK, n0);
+      uint32_t stage = 0, phase = 0;
+      for (int t = 1; t < T; ++t) {
+        const int tprev = (z == 0) ? (t - 1) : (T - t);   // time index holding h_{t-1} of this direction
+        const int col0 = tprev * 2 * H + z * H;
+        for (int half = 0; half < 2; ++half) {
+          // all NT column tiles of this (direction, row-half) must have published h_{t-1}
+          const unsigned int need = (unsigned int)NT * (unsigned int)t;
+          uint32_t spin = 0;
+          while (ld_acquire_gpu(flag0 + half) < need) {
+            if (++spin > (1u << 24)) {
+              printf("vc::lstm_persistent flag timeout (block %d,%d,%d step %d half %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, t, half);
+              __trap();
+            }
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");   // order the acquire before the async-proxy loads
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_expect_tx(fb, kBoxBytes);
+            tma_load_2d(smem_u32(a_s + (size_t)stage * kBoxBytes), &maps.out_ld, fb, col0 + kb * BK, m0 + half * 128);
+            if (++stage == kPlStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    if (lane == 0) {
+      // ===== input-projection tile of (step, row-half) =====
+      for (int t = 0; t < T; ++t) {
+        const int tt = (z == 0) ? t : (T - 1 - t);
+        for (int half = 0; half < 2; ++half) {
+          // the buffer is free once the previous tile -- (t, half 0) or (t-1, half 1) -- has been consumed
+          if (half == 1) mbar_wait(smem_u32(&xp_empty[0]), (uint32_t)(t & 1));
+          else if (t > 0) mbar_wait(smem_u32(&xp_empty[1]), (uint32_t)((t - 1) & 1));
+          const uint32_t xb = smem_u32(&xp_full[half]);
+          mbar_expect_tx(xb, 2 * kBoxBytes);
+          const int col = tt * 8 * H + z * 4 * H + n0;
+          tma_load_2d(smem_u32(xp_s), &maps.xp, xb, col, m0 + half * 128);
+          tma_load_2d(smem_u32(xp_s + kBoxBytes), &maps.xp, xb, col + 64, m0 + half * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(kPlBN);
+      mbar_wait(smem_u32(&w_bar), 0);
+      uint32_t stage = 0, phase = 0;
+      for (int t = 1; t < T; ++t) {
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(smem_u32(&tmem_empty[half]), (uint32_t)(((t - 1) & 1) ^ 1));   // epilogue drained this accumulator
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)(half * 128);
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            const uint64_t da = make_smem_desc(smem_u32(a_s + (size_t)stage * kBoxBytes));
+            const uint64_t db = make_smem_desc(smem_u32(w_s + (size_t)kb * kBoxBytes));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(smem_u32(&empty_bar[stage]));
+            if (++stage == kPlStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(smem_u32(&tmem_full[half]));
+        }
+      }
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // ===== epilogue: fused LSTM cell, one row x 32 hidden units per thread =====
+    const int half = (warp - 2) >> 2;
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                          // row inside the half
+    const int et = (warp - 2 - half * 4) * 32 + lane;     // 0..127 inside the half
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+    const uint32_t hbox = smem_u32(h_s + (size_t)half * (128 * 64));
+    const uint32_t xs = smem_u32(xp_s);
+    float c[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) c[u] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int tt = (z == 0) ? t : (T - 1 - t);
+      mbar_wait(smem_u32(&xp_full[half]), (uint32_t)(t & 1));
+      if (t > 0) {
+        mbar_wait(smem_u32(&tmem_full[half]), (uint32_t)((t - 1) & 1));
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        uint32_t v[32];
+        if (t > 0) {
+          tmem_ld32(taddr + (uint32_t)(ci * 32), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;        // h_{-1} = 0: gates = xproj + bias
+        }
+        float gte[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) gte[i] = __uint_as_float(v[i]) + bias_s[ci * 32 + i];
+        const uint32_t abox = xs + (uint32_t)(ci >> 1) * kBoxBytes;
+        const int ch0 = (ci & 1) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t w0, w1, w2, w3;
+          lds128(swz(abox, r, ch0 + k), w0, w1, w2, w3);
+          gte[8 * k + 0] += bf16_lo(w0); gte[8 * k + 1] += bf16_hi(w0);
+          gte[8 * k + 2] += bf16_lo(w1); gte[8 * k + 3] += bf16_hi(w1);
+          gte[8 * k + 4] += bf16_lo(w2); gte[8 * k + 5] += bf16_hi(w2);
+          gte[8 * k + 6] += bf16_lo(w3); gte[8 * k + 7] += bf16_hi(w3);
+        }
+        float hn[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float ig = sigmoid_<false>(gte[4 * u + 0]);
+          const float fg = sigmoid_<false>(gte[4 * u + 1]);
+          const float gg = tanh_<false>(gte[4 * u + 2]);
+          const float og = sigmoid_<false>(gte[4 * u + 3]);
+          const float cn = fmaf(fg, c[ci * 8 + u], ig * gg);
+          c[ci * 8 + u] = cn;
+          hn[u] = og * tanh_<false>(cn);
+        }
+        sts128(swz64(hbox, r, ci), pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]),
+               pack_bf16(hn[6], hn[7]));
+      }
+      if (t > 0) {
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tmem_empty[half]));         // accumulator may be overwritten by step t+1
+      }
+      mbar_arrive(smem_u32(&xp_empty[half]));             // input-projection tile consumed
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+      if (et == 0) {
+        tma_store_2d(&maps.out_st, hbox, tt * 2 * H + z * H + n0 / 4, m0 + half * 128);
+        tma_store_commit();
+        tma_store_wait_read();                            // staging box may be rewritten
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+      if (et == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // h_t slice is in global memory
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+        red_release_gpu_add(flag0 + half, 1u);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// box_cols x box_rows map with an explicit swizzle (the h store uses 32-column = 64-byte rows)
+inline int get_map_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                      uint32_t box_cols, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return VC_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (persistent LSTM) failed (%d)", (int)r);
+    return VC_ERR_CUDA;
+  }
+  return VC_OK;
+}
+
+inline size_t plstm_smem_bytes(int H) {
+  return (size_t)(H / BK) * kBoxBytes + (size_t)kPlStages * kBoxBytes + 2 * kBoxBytes + 2 * (128 * 64) + 1024;
+}
+
+// Largest batch one cooperative launch can take (0 = shape not supported by the persistent kernel).
+inline int plstm_max_batch(int H, int num_sms) {
+  if (H % BK != 0 || (4 * H) % kPlBN != 0 || plstm_smem_bytes(H) > 227 * 1024) return 0;
+  const int NT = 4 * H / kPlBN;
+  const int MT = num_sms / (2 * NT);
+  return MT * 256;
+}
+
+// One bidirectional layer, all T steps.  out: [B, T, 2H] bf16 (written), xp: [B, T, 8H] bf16 (both directions'
+// input projections incl. biases, gate-interleaved), W[dir]: [4H, H] bf16 gate-interleaved, flags: >= 4*MT uints.
+inline int launch_lstm_layer_persistent(bf16* out, const bf16* xp, const void* W0, const void* W1, int B, int T, int H,
+                                        unsigned int* flags, cudaStream_t stream) {
+  PLstmMaps mp;
+  VC_TRY(get_map(&mp.out_ld, out, (uint64_t)B, (uint64_t)T * 2 * H, (uint64_t)T * 2 * H, BM, 2));
+  VC_TRY(get_map_sw(&mp.out_st, out, (uint64_t)B, (uint64_t)T * 2 * H, (uint64_t)T * 2 * H, 128, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  VC_TRY(get_map(&mp.W[0], W0, (uint64_t)4 * H, (uint64_t)H, (uint64_t)H, 128, 2));
+  VC_TRY(get_map(&mp.W[1], W1, (uint64_t)4 * H, (uint64_t)H, (uint64_t)H, 128, 2));
+  VC_TRY(get_map(&mp.xp, xp, (uint64_t)B, (uint64_t)T * 8 * H, (uint64_t)T * 8 * H, BM, 2));
+  PLstmArgs a;
+  a.B = B; a.T = T; a.H = H;
+  a.bias[0] = a.bias[1] = nullptr;
+  a.flags = flags;
+  const int NT = 4 * H / kPlBN, MT = (B + 255) / 256;
+  VC_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * (size_t)4 * MT, stream));
+  const size_t smem = plstm_smem_bytes(H);
+  VC_CUDA(cudaFuncSetAttribute(lstm_layer_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(NT, MT, 2);
+  void* args[] = {(void*)&mp, (void*)&a};
+  VC_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_layer_persistent_kernel, grid, dim3(kPlThreads), args, smem, stream));
+  return VC_OK;
+}
+
+}  // namespace tc
+}  // namespace vc
