@@ -61,6 +61,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   printf("vc::tc mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
   __trap();
 }
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -398,6 +401,233 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs g) {
   }
 }
 
+// ---------------------------------------------------------------- persistent variant (large GEMMs)
+// Same roles and epilogues, but each CTA loops over output tiles (static round-robin, n fastest so CTAs that
+// run together share the A rows in L2), the smem ring keeps streaming across tile boundaries, and TWO TMEM
+// accumulators (2 x 256 columns) let the epilogue of tile i overlap the tcgen05 main loop of tile i+1.
+// No per-tile prologue, no wave quantisation.  BN = 256 only; EPI_LSTM without the addend (decoder form).
+//   EPI_STORE smem: kStages x 48 KB ring + 2 alternating 16 KB staging boxes
+//   EPI_LSTM  smem: kStages x 48 KB ring + c tile (2 boxes, in place) + h staging box
+template <int kStages, int EPI, class OutT, bool TANH>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, const int tiles_m, const int tiles_n) {
+  constexpr int BN = 256;
+  constexpr uint32_t kABytes = BM * BK * 2;
+  constexpr uint32_t kBBytes = BN * BK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* io_smem = smem + (size_t)kStages * kStageBytes;   // STORE: 2 staging boxes; LSTM: c box0, c box1, h box
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
+  __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2], c_full, c_empty;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float bias_s[2][BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const CUtensorMap* mapA = &maps.A[0];
+  const CUtensorMap* mapW = &maps.W[0];
+  const int nkb = g.K / BK;
+  const int num_tiles = tiles_m * tiles_n;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full[a]), 1);
+      mbar_init(smem_u32(&tmem_empty[a]), 128);
+    }
+    mbar_init(smem_u32(&c_full), 1);
+    mbar_init(smem_u32(&c_empty), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(mapW) : "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, kStageBytes);
+          const int k = kb * BK;
+          const int acol = g.a_col0[0] + k + (k >= g.a_split ? g.a_skip : 0);
+          uint8_t* sa = smem + (size_t)stage * kStageBytes;
+          tma_load_2d(smem_u32(sa), mapA, fb, acol, m0);
+          tma_load_2d(smem_u32(sa + kABytes), mapW, fb, k, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (EPI == EPI_LSTM) {
+          // previous cell state of this tile, needed only by epilogue(it): issued AFTER the operand loads so
+          // waiting for epilogue(it-1) to release the buffer never delays main loop(it)
+          mbar_wait(smem_u32(&c_empty), (uint32_t)((it & 1) ^ 1));
+          const uint32_t cb = smem_u32(&c_full);
+          mbar_expect_tx(cb, 2 * kBoxBytes);
+          tma_load_2d(smem_u32(io_smem), &maps.io[1], cb, g.io_col0[1][0] + n0 / 4, m0);
+          tma_load_2d(smem_u32(io_smem + kBoxBytes), &maps.io[1], cb, g.io_col0[1][0] + n0 / 4 + 32, m0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(BN);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int a = it & 1;
+        mbar_wait(smem_u32(&tmem_empty[a]), (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained accumulator a
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          uint8_t* sa = smem + (size_t)stage * kStageBytes;
+          const uint64_t da = make_smem_desc(smem_u32(sa));
+          const uint64_t db = make_smem_desc(smem_u32(sa + kABytes));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tmem_full[a]));
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int a = it & 1;
+      float* bs = bias_s[a];
+      for (int i = et; i < BN; i += 128) {
+        const int col = n0 + i;
+        bs[i] = (g.bias[0] != nullptr && col < g.N) ? g.bias[0][col] : 0.f;
+      }
+      if (EPI == EPI_LSTM) mbar_wait(smem_u32(&c_full), (uint32_t)(it & 1));
+      mbar_wait(smem_u32(&tmem_full[a]), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      epi_bar_sync();                                  // bias staged by all
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
+
+      if (EPI == EPI_STORE) {
+        constexpr int kColsPerBox = 128 / (int)sizeof(OutT);
+        constexpr int kLdPerBox = kColsPerBox / 32;
+        constexpr int kBoxes = BN / kColsPerBox;
+#pragma unroll 1
+        for (int bx = 0; bx < kBoxes; ++bx) {
+          const uint32_t box = smem_u32(io_smem) + (uint32_t)(bx & 1) * kBoxBytes;
+          // the staging box written two boxes ago must have been read by its store
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          epi_bar_sync();
+#pragma unroll
+          for (int h = 0; h < kLdPerBox; ++h) {
+            const int c = bx * kColsPerBox + h * 32;
+            uint32_t v[32];
+            tmem_ld32(taddr + (uint32_t)c, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              f[j] = __uint_as_float(v[j]) + bs[c + j];
+              if (TANH) f[j] = tanh_<false>(f[j]);
+            }
+            if (sizeof(OutT) == 4) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts128(swz(box, r, j), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                       __float_as_uint(f[4 * j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                sts128(swz(box, r, h * 4 + j), pack16<OutT>(f[8 * j], f[8 * j + 1]), pack16<OutT>(f[8 * j + 2], f[8 * j + 3]),
+                       pack16<OutT>(f[8 * j + 4], f[8 * j + 5]), pack16<OutT>(f[8 * j + 6], f[8 * j + 7]));
+            }
+          }
+          if (bx == kBoxes - 1) {                       // all TMEM reads of this accumulator are done
+            tc_fence_before();
+            mbar_arrive_cta(smem_u32(&tmem_empty[a]));
+          }
+          fence_proxy_async_smem();
+          epi_bar_sync();
+          if (et == 0) {
+            const int col = n0 + bx * kColsPerBox;
+            if (col < g.N) tma_store_2d(&maps.io[0], box, g.io_col0[0][0] + col, m0);
+            tma_store_commit();
+          }
+        }
+      } else {
+        const uint32_t c_s = smem_u32(io_smem);
+        const uint32_t h_box = smem_u32(io_smem + 2 * kBoxBytes);
+#pragma unroll 1
+        for (int ci = 0; ci < BN / 32; ++ci) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)(ci * 32), v);
+          tmem_ld_wait();
+          const int u0 = ci * 8;
+          const uint32_t cbox = c_s + (uint32_t)(u0 / 32) * kBoxBytes;
+          const int cch = (u0 % 32) / 4;
+          uint32_t cw[8];
+          lds128(swz(cbox, r, cch), cw[0], cw[1], cw[2], cw[3]);
+          lds128(swz(cbox, r, cch + 1), cw[4], cw[5], cw[6], cw[7]);
+          float hn[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float ig = sigmoid_<false>(__uint_as_float(v[4 * u + 0]) + bs[ci * 32 + 4 * u + 0]);
+            const float fg = sigmoid_<false>(__uint_as_float(v[4 * u + 1]) + bs[ci * 32 + 4 * u + 1]);
+            const float gg = tanh_<false>(__uint_as_float(v[4 * u + 2]) + bs[ci * 32 + 4 * u + 2]);
+            const float og = sigmoid_<false>(__uint_as_float(v[4 * u + 3]) + bs[ci * 32 + 4 * u + 3]);
+            const float cn = fmaf(fg, __uint_as_float(cw[u]), ig * gg);
+            hn[u] = og * tanh_<false>(cn);
+            cw[u] = __float_as_uint(cn);
+          }
+          sts128(swz(cbox, r, cch), cw[0], cw[1], cw[2], cw[3]);
+          sts128(swz(cbox, r, cch + 1), cw[4], cw[5], cw[6], cw[7]);
+          sts128(swz(h_box, r, ci), pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]),
+                 pack_bf16(hn[6], hn[7]));
+        }
+        tc_fence_before();
+        mbar_arrive_cta(smem_u32(&tmem_empty[a]));
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (et == 0) {
+          const int u_tile = n0 / 4;
+          tma_store_2d(&maps.io[3], h_box, g.io_col0[3][0] + u_tile, m0);
+          if (g.has_h1) tma_store_2d(&maps.io[4], h_box, g.io_col0[4][0] + u_tile, m0);
+          tma_store_2d(&maps.io[2], c_s, g.io_col0[2][0] + u_tile, m0);
+          tma_store_2d(&maps.io[2], c_s + kBoxBytes, g.io_col0[2][0] + u_tile + 32, m0);
+          tma_store_commit();
+          tma_store_wait_read();
+          mbar_arrive_cta(smem_u32(&c_empty));          // c / h boxes may be refilled for the next tile
+        }
+        epi_bar_sync();                                 // nobody rewrites h_box before the stores have read it
+      }
+    }
+    if (et == 0) tma_store_wait_read();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------- legacy direct-store kernel
 // Generic functor epilogue with row-per-thread global accesses: slow, kept only for the cases the staged
 // epilogue does not cover (packed-sequence masking, a second fp32 output, unaligned pitches).
@@ -586,6 +816,16 @@ inline int ref_map(CUtensorMap* out, int* col0, const Ref& r, uint64_t rows, uin
   return get_map(out, o, rows, (uint64_t)r.cols, (uint64_t)r.ld, box_rows, esize);
 }
 
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else n = 148;
+  }
+  return n;
+}
+
 inline bool tma_ok(const void* p, int64_t ld, int esize) {
   return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * esize) % 16 == 0;
 }
@@ -635,12 +875,15 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
   ta.bias[0] = ta.bias[1] = e.bias[0];
   VC_TRY(get_map(&mp.io[0], e.C[0], (uint64_t)g.M, (uint64_t)g.N, (uint64_t)e.ldc, BM, sizeof(OutT)));
   if (BN == 256) {
-    constexpr int kStages = 4;
-    const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 1024;
-    auto kern = gemm_tc_kernel<256, kStages, 1, EPI_STORE, OutT, TANH, false>;
+    // persistent, TMEM double-buffered: one CTA per SM loops over the tiles
+    // (4 stages + staging + static smem would exceed the 227 KB limit by 128 bytes)
+    constexpr int kStages = 3;
+    const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 2 * kBoxBytes + 1024;
+    auto kern = gemm_tc_persistent_kernel<kStages, EPI_STORE, OutT, TANH>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((g.N + 255) / 256, (g.M + BM - 1) / BM, 1);
-    kern<<<grid, kThreads, smem, stream>>>(mp, ta);
+    const int tm = (g.M + BM - 1) / BM, tn = (g.N + 255) / 256;
+    const int ctas = tm * tn < num_sms() ? tm * tn : num_sms();
+    kern<<<ctas, kThreads, smem, stream>>>(mp, ta, tm, tn);
   } else {
     // 3 stages x 32 KB: two CTAs co-reside per SM, so one CTA's epilogue overlaps the other's main loop
     constexpr int kStages = 3;
@@ -684,6 +927,15 @@ inline int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiLstm<bf16,
     }
   }
   dim3 grid(g.N / 256, (g.M + BM - 1) / BM, g.nz);
+  if (!has_add && g.nz == 1 && (int)(grid.x * grid.y) >= num_sms()) {
+    constexpr int kStages = 3;
+    const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 3 * kBoxBytes + 1024;
+    auto kern = gemm_tc_persistent_kernel<kStages, EPI_LSTM, bf16, false>;
+    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<num_sms(), kThreads, smem, stream>>>(mp, ta, (int)grid.y, (int)grid.x);
+    VC_CUDA(cudaGetLastError());
+    return VC_OK;
+  }
   if (has_add) {
     constexpr int kStages = 2;
     const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + (size_t)(4 + 2) * kBoxBytes + 1024;
