@@ -289,3 +289,32 @@ def test_host_feature_ingest_matches_device_path():
     # pageable (non-pinned) host memory also works, just slower
     c = m.generate(host.clone(), START, END, max_length=9, method="greedy")
     assert torch.equal(c["generated_tokens"], m.generate(dev, START, END, max_length=9)["generated_tokens"])
+
+
+# ------------------------------------------------------------------ fused selection (vocab-GEMM statistics) == streaming selection
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,V,B,K", [("tiny", 1000, 9, 5), ("tiny", 2500, 5, 3), ("small", 10000, 6, 5),
+                                         ("tiny", 30000, 4, 5), ("tiny", 1000, 7, 1), ("small", 10000, 3, 8)])
+def test_fused_select_equals_streaming_select(monkeypatch, shape, V, B, K):
+    """bf16 mode: the selection that reads the vocab GEMM's chunk maxima / log-sum-exp partials must pick exactly the
+    tokens, lengths and scores of the selection that streams the whole logits row (identical logits, same tie
+    order), for beam (video_captioning_model.py:209-272) and greedy (decoder.py:269).  Vocab sizes cover a ragged
+    last tile, one chunk-array instantiation each (nc <= 384 / nc <= 1024) and END-staggered stops."""
+    from oracle import synth
+    cfg = synth.make_config(shape, V=V)
+    sd = synth.make_state_dict(cfg, V, "bahdanau", seed=11, logit_gain=8.0, end_token_id=END, end_bias=0.5)
+    T, F = cfg.model.video_sequence_length, cfg.model.cnn_feature_dim
+    x = torch.from_numpy(synth.make_features(B, T, F, seed=4)).cuda()
+    outs = []
+    for disable in ("1", "0"):
+        monkeypatch.setenv("VC_DISABLE_FUSED_SELECT", disable)      # read when the native handle is created
+        m = make_native_model(cfg, V, sd, "bahdanau", "bf16")
+        bm = m.generate(x, START, END, max_length=12, method="beam", beam_size=K)
+        gr = m.generate(x, START, END, max_length=12, method="greedy")
+        torch.cuda.synchronize()
+        outs.append((bm["generated_tokens"].cpu(), bm["lengths"].cpu(), bm["scores"].cpu() if "scores" in bm else None,
+                     gr["generated_tokens"].cpu()))
+    (t0, l0, s0, g0), (t1, l1, s1, g1) = outs
+    assert torch.equal(t0, t1) and torch.equal(l0, l1) and torch.equal(g0, g1)
+    if s0 is not None:
+        assert torch.allclose(s0, s1, rtol=1e-5, atol=1e-5)     # log-sum-exp merged in a different order

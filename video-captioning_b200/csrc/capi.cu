@@ -114,6 +114,8 @@ struct vc_model {
   bool finalized = false;
   int num_sms = 148;
   bool disable_persistent_lstm = false;   // VC_DISABLE_PERSISTENT_LSTM=1: per-timestep launches (A/B testing)
+  int dbg_vocab = 0;                      // VC_DEBUG_VOCAB: timing experiments (gemm_tc.cuh VocabStats::dbg), results invalid
+  bool disable_fused_select = false;      // VC_DISABLE_FUSED_SELECT=1: stream the whole logits row in the selection (A/B testing)
   // derived, operand-typed (float or bf16 according to d.precision)
   void* Wp = nullptr; float* bp = nullptr;
   void* enc_Wih[4] = {}; float* enc_bias[4] = {};
@@ -317,6 +319,8 @@ struct WS {
   float *cst, *final_f32;
   ActT *Z, *XL[4], *Hn[4], *ctx_pre, *O;
   float *C[4], *Cn[4], *Q, *logits, *cand_val, *scores, *best_score;
+  float* vs_cmax;        // vocab GEMM statistics (gemm_tc.cuh VocabStats): [R, nc] chunk maxima
+  float2* vs_part;       // [R, np] log-sum-exp partials
   int *cand_idx, *parent, *cur_tok, *done, *best_len, *best_seq, *hist[2];
   unsigned char* alive;
   size_t total;
@@ -354,6 +358,11 @@ WS<ActT> carve(const vc_model_desc_t& d, void* base, int B, int T, int K, int S)
   w.ctx_pre = c.take<ActT>(R * H);
   w.O = c.take<ActT>(R * H);
   w.logits = c.take<float>(R * V);
+  {
+    const size_t tn = (V + 255) / 256;
+    w.vs_cmax = c.take<float>(R * 8 * tn);
+    w.vs_part = c.take<float2>(R * 2 * tn);
+  }
   w.cand_val = c.take<float>(R * K);
   w.cand_idx = c.take<int>(R * K);
   w.parent = c.take<int>(R);
@@ -371,6 +380,12 @@ WS<ActT> carve(const vc_model_desc_t& d, void* base, int B, int T, int K, int S)
 }
 
 // ---------------------------------------------------------------- GEMM dispatch
+// vocabulary projection with the selection statistics (bf16 mode only)
+inline int gemm_vocab_stats(const GemmArgs& g, int64_t a_cols, const EpiStore<float, false, false>& e, cudaStream_t s,
+                            const tc::VocabStats& vs) {
+  return tc::launch_gemm_tc(g, a_cols, e, s, &vs);
+}
+
 template <class ActT, class Epi>
 int gemm(const GemmArgs& g, int64_t a_cols, const Epi& e, cudaStream_t s) {
   if constexpr (std::is_same<ActT, float>::value) {
@@ -684,13 +699,36 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
     // vocabulary projection (:169)
     float* lg = (mode == DM_TEACHER) ? teacher_logits + (size_t)step * V : w.logits;
     const int64_t ldl = (mode == DM_TEACHER) ? (int64_t)S * V : V;
+    const int vtn = (V + 255) / 256;
+    // bf16 mode: the GEMM epilogue also emits per-row chunk maxima + log-sum-exp partials, and the selection
+    // reads those instead of the whole logits row (decode.cuh: select_fused_kernel)
+    const bool fused_sel = !P && mode != DM_TEACHER && !m->disable_fused_select && V >= 256 && 8 * vtn <= 1024 &&
+                           (mode == DM_BEAM || p.temperature == 1.0f);
     {
       VC_SCOPE(VC_CLS_DEC_VOCAB);
-      VC_TRY((gemm<ActT>(gargs(w.O, H, m->Wv, H, R, V, H), H, estore<float, false, P>(lg, ldl, m->bv), s)));
+      if constexpr (!P) {
+        if (fused_sel) {
+          tc::VocabStats vs;
+          memset(&vs, 0, sizeof(vs));
+          vs.cmax = w.vs_cmax; vs.part = w.vs_part; vs.nc = 8 * vtn; vs.np = 2 * vtn;
+          vs.dbg = m->dbg_vocab;
+          vs.topk = K <= 8 ? K : 0;     // chunks that cannot be among the row's K best are never written
+          VC_TRY(gemm_vocab_stats(gargs(w.O, H, m->Wv, H, R, V, H), H, estore<float, false, false>(lg, ldl, m->bv), s, vs));
+        } else {
+          VC_TRY((gemm<ActT>(gargs(w.O, H, m->Wv, H, R, V, H), H, estore<float, false, P>(lg, ldl, m->bv), s)));
+        }
+      } else {
+        VC_TRY((gemm<ActT>(gargs(w.O, H, m->Wv, H, R, V, H), H, estore<float, false, P>(lg, ldl, m->bv), s)));
+      }
     }
     // selection
     const int* parent = nullptr;
-    if (mode == DM_GREEDY) {
+    if (fused_sel) {
+      VC_SCOPE(VC_CLS_SELECT);
+      VC_TRY(launch_select_fused(bs, lg, ldl, w.vs_cmax, w.vs_part, 8 * vtn, 2 * vtn, B, K, V, S, step, p.end_token_id,
+                                 p.length_penalty, w.parent, w.cur_tok, mode == DM_GREEDY ? 1 : 0, tokens_out, s));
+      if (mode == DM_BEAM) parent = w.parent;
+    } else if (mode == DM_GREEDY) {
       VC_SCOPE(VC_CLS_SELECT);
       greedy_argmax_kernel<<<R, 256, 0, s>>>(lg, ldl, V, p.temperature == 1.0f ? 1.f : 0.f, p.temperature, w.cur_tok,
                                              tokens_out, S, step);
@@ -806,6 +844,10 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   cudaGetLastError();   // creating a handle must also work where no device is visible (CPU-side tests)
   const char* env = getenv("VC_DISABLE_PERSISTENT_LSTM");
   m->disable_persistent_lstm = env != nullptr && env[0] == '1';
+  env = getenv("VC_DEBUG_VOCAB");
+  m->dbg_vocab = env != nullptr ? atoi(env) : 0;
+  env = getenv("VC_DISABLE_FUSED_SELECT");
+  m->disable_fused_select = env != nullptr && env[0] == '1';
   *out = m;
   return VC_OK;
 }

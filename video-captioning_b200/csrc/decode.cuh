@@ -333,33 +333,38 @@ struct BeamState {
 
 constexpr int kSelWarps = 4;   // videos per CTA (one warp each)
 
-__global__ void __launch_bounds__(kSelWarps * 32) beam_select_kernel(
-    BeamState bs, const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int B, int K, int V, int S, int step,
-    int end_id, float length_penalty, int* __restrict__ parent /*[R]*/, int* __restrict__ cur_tok /*[R]*/) {
-  __shared__ float s_v[kSelWarps][16], s_ns[kSelWarps][16];
-  __shared__ int s_pk[kSelWarps][16], s_nt[kSelWarps][16];    // selection order: parent beam, token
-  __shared__ int s_np[kSelWarps][16], s_tk[kSelWarps][16];    // compacted live beams: parent beam, token
-  __shared__ int s_misc[kSelWarps][4];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int b = blockIdx.x * kSelWarps + w;
-  if (b >= B) return;                       // warp-uniform
+// Per-warp scratch of the selection (shared memory).
+struct SelScratch {
+  float v[16], ns[16];
+  int pk[16], nt[16];     // selection order: parent beam, token
+  int np[16], tk[16];     // compacted live beams: parent beam, token
+  int misc[4];
+};
+
+// One warp selects for one video.  cand_val / cand_idx: the video's [K][K] per-row candidates (row k's j-th best
+// log-prob and token), in global or shared memory.
+template <int NQ>   // candidate slots per lane: K*K <= 32*NQ
+__device__ __forceinline__ void beam_select_video(const BeamState& bs, const float* cand_val, const int* cand_idx,
+                                                  SelScratch& sm, int b, int K, int V, int S, int step, int end_id,
+                                                  float length_penalty, int* __restrict__ parent, int* __restrict__ cur_tok) {
+  const int lane = threadIdx.x & 31;
   const int* hin = bs.hist[step & 1];
   int* hout = bs.hist[(step + 1) & 1];
   const int r0 = b * K, KK = K * K;
 
   // candidates c = k*K + j (beam k, its j-th best token): lane owns c = lane + 32*q
-  float cv[8];
-  int cf[8];
+  float cv[NQ];
+  int cf[NQ];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < NQ; ++q) {
     const int c = lane + 32 * q;
     cv[q] = -INFINITY;
     cf[q] = 0x7fffffff;
     if (c < KK) {
       const int k = c / K;
       if (bs.alive[r0 + k]) {
-        cv[q] = bs.scores[r0 + k] + cand_val[(int64_t)(r0 + k) * K + (c - k * K)];       // :211
-        cf[q] = k * V + cand_idx[(int64_t)(r0 + k) * K + (c - k * K)];                   // flat index of :215
+        cv[q] = bs.scores[r0 + k] + cand_val[c];                                          // :211
+        cf[q] = k * V + cand_idx[c];                                                      // flat index of :215
       }
     }
   }
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(kSelWarps * 32) beam_select_kernel(
     float bv = -INFINITY;
     int bf = 0x7fffffff, bq = -1;
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < NQ; ++q)
       if (cf[q] != 0x7fffffff && (bq < 0 || cv[q] > bv || (cv[q] == bv && cf[q] < bf))) { bv = cv[q]; bf = cf[q]; bq = q; }
     float wv = bv;
     int wf = bf;
@@ -382,11 +387,11 @@ __global__ void __launch_bounds__(kSelWarps * 32) beam_select_kernel(
     if (wf == 0x7fffffff) break;            // no live candidate left (warp-uniform)
     if (bq >= 0 && bf == wf) {              // flat indices are unique: exactly one owner
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
+      for (int q = 0; q < NQ; ++q)
         if (q == bq) cf[q] = 0x7fffffff;
-      s_v[w][sel] = wv;
-      s_pk[w][sel] = wf / V;                // :219
-      s_nt[w][sel] = wf % V;                // :220
+      sm.v[sel] = wv;
+      sm.pk[sel] = wf / V;                  // :219
+      sm.nt[sel] = wf % V;                  // :220
     }
     ++n_sel;
   }
@@ -397,44 +402,207 @@ __global__ void __launch_bounds__(kSelWarps * 32) beam_select_kernel(
     float best_score = bs.best_score[b];
     int best_len = bs.best_len[b];
     for (int sel = 0; sel < n_sel; ++sel) {
-      const int pk = s_pk[w][sel], tok = s_nt[w][sel];
-      const float v = s_v[w][sel];
+      const int pk = sm.pk[sel], tok = sm.nt[sel];
+      const float v = sm.v[sel];
       if (tok == end_id) {
         const float fin = v / (float)pow((double)(step + 1), (double)length_penalty);   // (len(new_seq)-1)**lp, :238-239
         if (best_len == 0 || fin > best_score) { best_score = fin; best_len = step + 1; best_pk = pk; best_tok = tok; }
       } else {
-        s_np[w][n_alive] = pk;
-        s_ns[w][n_alive] = v;
-        s_tk[w][n_alive] = tok;
+        sm.np[n_alive] = pk;
+        sm.ns[n_alive] = v;
+        sm.tk[n_alive] = tok;
         ++n_alive;
       }
     }
     if (best_pk >= 0) { bs.best_score[b] = best_score; bs.best_len[b] = best_len; }
-    s_misc[w][0] = n_alive;
-    s_misc[w][1] = best_pk;
-    s_misc[w][2] = best_tok;
+    sm.misc[0] = n_alive;
+    sm.misc[1] = best_pk;
+    sm.misc[2] = best_tok;
     if (n_alive == 0) bs.done[b] = 1;       // :251
   }
   __syncwarp();
-  const int n_alive = s_misc[w][0], best_pk = s_misc[w][1];
+  const int n_alive = sm.misc[0], best_pk = sm.misc[1];
   if (best_pk >= 0) {
     for (int i = lane; i < step; i += 32) bs.best_seq[(int64_t)b * S + i] = hin[(int64_t)(r0 + best_pk) * S + i];
-    if (lane == 0) bs.best_seq[(int64_t)b * S + step] = s_misc[w][2];
+    if (lane == 0) bs.best_seq[(int64_t)b * S + step] = sm.misc[2];
   }
   for (int k = 0; k < K; ++k) {
     const int r = r0 + k;
     const bool live = k < n_alive;
-    const int src = live ? r0 + s_np[w][k] : r;       // dead slot: keeps computing on benign inputs
-    const int tok = live ? s_tk[w][k] : end_id;
+    const int src = live ? r0 + sm.np[k] : r;         // dead slot: keeps computing on benign inputs
+    const int tok = live ? sm.tk[k] : end_id;
     for (int i = lane; i < step; i += 32) hout[(int64_t)r * S + i] = hin[(int64_t)src * S + i];
     if (lane == 0) {
       hout[(int64_t)r * S + step] = tok;
-      bs.scores[r] = live ? s_ns[w][k] : -INFINITY;
+      bs.scores[r] = live ? sm.ns[k] : -INFINITY;
       bs.alive[r] = live ? 1 : 0;
       parent[r] = src;
       cur_tok[r] = tok;
     }
   }
+}
+
+__global__ void __launch_bounds__(kSelWarps * 32) beam_select_kernel(
+    BeamState bs, const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int B, int K, int V, int S, int step,
+    int end_id, float length_penalty, int* __restrict__ parent /*[R]*/, int* __restrict__ cur_tok /*[R]*/) {
+  __shared__ SelScratch scratch[kSelWarps];
+  const int w = threadIdx.x >> 5;
+  const int b = blockIdx.x * kSelWarps + w;
+  if (b >= B) return;                       // warp-uniform
+  if (K * K <= 32)
+    beam_select_video<1>(bs, cand_val + (int64_t)b * K * K, cand_idx + (int64_t)b * K * K, scratch[w], b, K, V, S, step, end_id,
+                         length_penalty, parent, cur_tok);
+  else
+    beam_select_video<8>(bs, cand_val + (int64_t)b * K * K, cand_idx + (int64_t)b * K * K, scratch[w], b, K, V, S, step, end_id,
+                         length_penalty, parent, cur_tok);
+}
+
+// ---------------------------------------------------------------- fused selection from the vocab GEMM's statistics
+// bf16 mode.  The vocabulary GEMM's epilogue (gemm_tc.cuh, STATS) leaves, per row, the maximum of every
+// 32-column chunk of the logits and a (max, sum exp) pair per 128 columns.  Every element of a row's top-K
+// (order: value desc, vocabulary index asc) lies in one of the K chunks with the largest maxima (ties: lower
+// chunk first): if it did not, K chunk maxima -- K distinct elements -- would precede it.  So one warp per row
+//   1. merges the log-sum-exp partials                               (video_captioning_model.py:209)
+//   2. picks the K best chunks from the nc maxima,
+//   3. reads those K x 128 bytes of logits and takes the exact top-K (:215, first half),
+// and then warp 0 of the CTA (one CTA per video) runs the per-video selection (:211-272) on the K x K
+// candidates through shared memory.  Greedy mode (K = 1, decoder.py:269): the top-1 is the next token.
+// HBM traffic per row: (nc + 2 np) * 4 + K * 128 bytes instead of 4 * V.
+// KMAX: compile-time bound of the beam size (loops are unrolled to it); MAXCL: chunk maxima per lane held in
+// registers (nc <= 32 * MAXCL).
+template <int KMAX, int MAXCL>
+__global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, const float* __restrict__ logits, int64_t ld,
+                                                                 const float* __restrict__ cmax, const float2* __restrict__ part,
+                                                                 int nc, int np, int B, int K, int V, int S, int step, int end_id,
+                                                                 float length_penalty, int* __restrict__ parent,
+                                                                 int* __restrict__ cur_tok, int greedy, int* __restrict__ tokens_out) {
+  __shared__ float s_cv[KMAX * KMAX];
+  __shared__ int s_ci[KMAX * KMAX];
+  __shared__ SelScratch scratch;
+  const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;     // warp k <-> beam row k of video b
+  const int b = blockIdx.x;
+  const int64_t r = (int64_t)b * K + k;
+  constexpr float kL2e = 1.4426950408889634f;
+
+  // chunk maxima first (the longest dependent chain starts here)
+  float cv[MAXCL];
+#pragma unroll
+  for (int i = 0; i < MAXCL; ++i) {
+    const int c = lane + 32 * i;
+    cv[i] = (c < nc) ? __ldg(cmax + r * nc + c) : -INFINITY;
+  }
+  // 1. log-sum-exp of the row
+  float lse;
+  {
+    float2 p[3];
+    float m = -1e30f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int j = lane + 32 * i;
+      p[i] = (j < np) ? __ldg(part + r * np + j) : make_float2(-1e30f, 0.f);
+      m = fmaxf(m, p[i].x);
+    }
+    for (int j = lane + 96; j < np; j += 32) m = fmaxf(m, __ldg(part + r * np + j).x);
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sum += p[i].y * exp2f((p[i].x - m) * kL2e);
+    for (int j = lane + 96; j < np; j += 32) {
+      const float2 pp = __ldg(part + r * np + j);
+      sum += pp.y * exp2f((pp.x - m) * kL2e);
+    }
+    sum = warp_sum(sum);
+    lse = m + logf(sum);
+  }
+  // 2. K best chunks; 3a. this lane's element of each
+  float val[KMAX];
+  int cidx[KMAX];
+#pragma unroll
+  for (int sel = 0; sel < KMAX; ++sel) {
+    val[sel] = -INFINITY;
+    cidx[sel] = 0x7fffffff;
+    if (sel < K) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < MAXCL; ++i)
+        if (cv[i] > bv) { bv = cv[i]; bi = lane + 32 * i; }     // ascending i: the first maximum has the lowest chunk index
+      float wv = bv;
+      int wi = bi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float tv = __shfl_xor_sync(0xffffffffu, wv, o);
+        const int ti = __shfl_xor_sync(0xffffffffu, wi, o);
+        if (tv > wv || (tv == wv && ti < wi)) { wv = tv; wi = ti; }
+      }
+#pragma unroll
+      for (int i = 0; i < MAXCL; ++i)
+        if (lane + 32 * i == wi) cv[i] = -INFINITY;
+      if (wi != 0x7fffffff) {
+        const int col = wi * 32 + lane;
+        cidx[sel] = col;
+        if (col < V) val[sel] = __ldg(logits + r * ld + col);
+      }
+    }
+  }
+  // 3b. exact top-K of the K x 32 candidates: K rounds of (lane-local best, warp arg-max, remove)
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    if (j < K) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int sel = 0; sel < KMAX; ++sel)
+        if (val[sel] > bv || (val[sel] == bv && val[sel] != -INFINITY && cidx[sel] < bi)) { bv = val[sel]; bi = cidx[sel]; }
+      float wv = bv;
+      int wi = bi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float tv = __shfl_xor_sync(0xffffffffu, wv, o);
+        const int ti = __shfl_xor_sync(0xffffffffu, wi, o);
+        if (tv > wv || (tv == wv && ti < wi)) { wv = tv; wi = ti; }
+      }
+#pragma unroll
+      for (int sel = 0; sel < KMAX; ++sel)
+        if (cidx[sel] == wi) val[sel] = -INFINITY;
+      if (lane == 0) {
+        s_cv[k * K + j] = wv - lse;          // log_softmax value of the j-th best token of row k
+        s_ci[k * K + j] = wi;
+      }
+    }
+  }
+  if (greedy) {
+    if (lane == 0) {
+      const int tok = s_ci[k * K];
+      cur_tok[r] = tok;
+      tokens_out[r * S + step] = tok;
+    }
+    return;
+  }
+  __syncthreads();
+  if (k == 0) beam_select_video<(KMAX * KMAX + 31) / 32>(bs, s_cv, s_ci, scratch, b, K, V, S, step, end_id, length_penalty, parent, cur_tok);
+}
+
+// host-side dispatch on (beam size, chunk count)
+inline int launch_select_fused(BeamState bs, const float* logits, int64_t ld, const float* cmax, const float2* part, int nc, int np,
+                               int B, int K, int V, int S, int step, int end_id, float lp, int* parent, int* cur_tok, int greedy,
+                               int* tokens_out, cudaStream_t s) {
+#define VC_SEL(KM, CL) select_fused_kernel<KM, CL><<<B, K * 32, 0, s>>>(bs, logits, ld, cmax, part, nc, np, B, K, V, S, step, end_id, lp, parent, cur_tok, greedy, tokens_out)
+#define VC_SEL_K(CL)                     \
+  do {                                   \
+    if (K == 1) VC_SEL(1, CL);           \
+    else if (K <= 3) VC_SEL(3, CL);      \
+    else if (K <= 5) VC_SEL(5, CL);      \
+    else if (K <= 8) VC_SEL(8, CL);      \
+    else VC_SEL(16, CL);                 \
+  } while (0)
+  VC_CHECK(K >= 1 && K <= 16 && nc <= 1024, "fused selection: K=%d nc=%d out of range", K, nc);
+  if (nc <= 320) VC_SEL_K(10);
+  else VC_SEL_K(32);
+#undef VC_SEL_K
+#undef VC_SEL
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
 }
 
 // ---------------------------------------------------------------- reorder (+ next-step embedding)

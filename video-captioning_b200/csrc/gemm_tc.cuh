@@ -406,18 +406,57 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs g) {
 // run together share the A rows in L2), the smem ring keeps streaming across tile boundaries, and TWO TMEM
 // accumulators (2 x 256 columns) let the epilogue of tile i overlap the tcgen05 main loop of tile i+1.
 // No per-tile prologue, no wave quantisation.  BN = 256 only; EPI_LSTM without the addend (decoder form).
-//   EPI_STORE smem: kStages x 48 KB ring + 2 alternating 16 KB staging boxes
-//   EPI_LSTM  smem: kStages x 48 KB ring + c tile (2 boxes, in place) + h staging box
-template <int kStages, int EPI, class OutT, bool TANH>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, const int tiles_m, const int tiles_n) {
+//   EPI_STORE: EIGHT epilogue warps = two column halves x four TMEM lane quarters (a 128x256 fp32 tile costs
+//              more epilogue time than tcgen05 time with four), each half with its own pair of alternating
+//              16 KB staging boxes.   smem: kStages x 48 KB ring + 4 staging boxes
+//   EPI_LSTM : four epilogue warps.   smem: kStages x 48 KB ring + c tile (2 boxes, in place) + h staging box
+//
+// STATS (vocabulary projection, fp32 logits; video_captioning_model.py:209 log_softmax, :215 topk;
+// decoder.py:269 argmax): the logits tile never goes through the staging boxes.  Per row the epilogue emits
+// the maximum of every 32-column chunk and a (max, sum exp) pair per 128-column half tile, and writes a
+// chunk's 32 logits to HBM ONLY IF the chunk can still belong to the row's `topk` best chunks: CTAs own
+// contiguous m-major tile ranges, every epilogue thread keeps the sorted `topk` largest chunk maxima it has
+// seen for its row in the current range, and a chunk is stored iff its maximum beats the topk-th of them
+// (strictly: on a tie the earlier chunk wins, matching the selection's value-desc / index-asc order).  A
+// chunk among the row's global top-`topk` chunks always passes (the range-local list is a subset), and
+// those are the only chunks the selection kernel (decode.cuh: select_fused_kernel) reads.  Expected stores:
+// ~topk*(1+ln(n/topk)) of the n chunks of a range, i.e. ~20% of the 4*V bytes per row; the plain fp32 store
+// of all logits was HBM-write bound (205 MB per step at the MSVD shape, 63 us vs 38 us of tcgen05 time).
+struct VocabStats {
+  float* cmax;      // [M, nc] maximum logit of each 32-column chunk (-inf for chunks past N)
+  float2* part;     // [M, np] (max, sum 2^((x-max)*log2e)) per 128-column half tile
+  int nc, np;       // nc = 8 * tiles_n, np = 2 * tiles_n
+  float* logits;    // [M, ld] fp32, sparsely written (see above)
+  int64_t ld;
+  int topk;         // 1..8: prune; 0: store every chunk
+  int dbg;          // timing experiments only (VC_DEBUG_VOCAB): 1 = skip the logits stores, 2 = skip the exp sums, 4 = skip stats stores
+};
+
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int EPI> struct PersistentCfg {
+  static constexpr int kEpiWarps = (EPI == EPI_STORE) ? 8 : 4;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+};
+
+template <int kStages, int EPI, class OutT, bool TANH, bool STATS>
+__global__ void __launch_bounds__(PersistentCfg<EPI>::kThreads, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, const int tiles_m, const int tiles_n,
+                          const VocabStats vstat) {
+  static_assert(!STATS || (EPI == EPI_STORE && sizeof(OutT) == 4 && !TANH), "STATS: fp32 logits store only");
   constexpr int BN = 256;
+  constexpr int kEpiThreads = 32 * PersistentCfg<EPI>::kEpiWarps;
   constexpr uint32_t kABytes = BM * BK * 2;
   constexpr uint32_t kBBytes = BN * BK * 2;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* io_smem = smem + (size_t)kStages * kStageBytes;   // STORE: 2 staging boxes; LSTM: c box0, c box1, h box
+  uint8_t* io_smem = smem + (size_t)kStages * kStageBytes;   // STORE: 4 staging boxes; LSTM: c box0, c box1, h box
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
   __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2], c_full, c_empty;
   __shared__ uint32_t tmem_base_slot;
@@ -428,6 +467,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
   const CUtensorMap* mapW = &maps.W[0];
   const int nkb = g.K / BK;
   const int num_tiles = tiles_m * tiles_n;
+  // tile schedule (m-major tile index, n fastest): round-robin, or contiguous ranges when the epilogue carries
+  // per-row state from tile to tile (STATS)
+  const int t_first = STATS ? (int)((int64_t)blockIdx.x * num_tiles / gridDim.x) : (int)blockIdx.x;
+  const int t_last = STATS ? (int)((int64_t)(blockIdx.x + 1) * num_tiles / gridDim.x) : num_tiles;
+  const int t_step = STATS ? 1 : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -436,7 +480,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full[a]), 1);
-      mbar_init(smem_u32(&tmem_empty[a]), 128);
+      mbar_init(smem_u32(&tmem_empty[a]), kEpiThreads);
     }
     mbar_init(smem_u32(&c_full), 1);
     mbar_init(smem_u32(&c_empty), 1);
@@ -455,7 +499,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       // ===== TMA producer =====
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
         const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -485,7 +529,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       constexpr uint32_t idesc = make_idesc(BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
         const int a = it & 1;
         mbar_wait(smem_u32(&tmem_empty[a]), (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained accumulator a
         tc_fence_after();
@@ -507,37 +551,160 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
     }
   } else {
     // ===== epilogue =====
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int et = threadIdx.x - 64;
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                          // row inside the tile
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-      const int a = it & 1;
-      float* bs = bias_s[a];
-      for (int i = et; i < BN; i += 128) {
-        const int col = n0 + i;
-        bs[i] = (g.bias[0] != nullptr && col < g.N) ? g.bias[0][col] : 0.f;
+    if constexpr (STATS) {
+      // warps 2..5 = column half 0, warps 6..9 = column half 1; thread = one row x 128 columns per tile
+      const int half = (warp - 2) >> 2;
+      const int eh = ((warp - 2) & 3) * 32 + lane;
+      const int bar_id = 1 + half;
+      constexpr int KS = 8;
+      const uint32_t wslot = smem_u32(io_smem) + (uint32_t)(warp - 2) * (32u * 144u);   // this warp's 32 row slots
+      const uint32_t slot = wslot + (uint32_t)lane * 144u;                             // 128 B + 16 B pad: conflict-free sts128
+      float top[KS];                                      // largest chunk maxima of this row in this tile range
+      float thr = -INFINITY;                              // the topk-th of them (chunks must beat it to be stored)
+      int cur_mb = -1;
+      for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
+        const int tmi = tile / tiles_n, tn = tile - tmi * tiles_n;
+        const int m0 = tmi * BM, n0 = tn * BN;
+        const int a = it & 1;
+        if (tmi != cur_mb) {
+          cur_mb = tmi;
+          thr = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < KS; ++j) top[j] = -INFINITY;
+        }
+        float* bs = bias_s[a] + half * 128;
+        {
+          const int col = n0 + half * 128 + eh;
+          bs[eh] = (g.bias[0] != nullptr && col < g.N) ? g.bias[0][col] : 0.f;
+        }
+        mbar_wait(smem_u32(&tmem_full[a]), (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // bias of this half staged
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + half * 128);
+        const bool tail_tile = n0 + BN > g.N;
+        const int row = m0 + r;
+        float run_m = -1e30f, run_s = 0.f;                // online (max, sum 2^((x-max) log2e)) of this half tile
+        float cm[4];
+#pragma unroll
+        for (int bx = 0; bx < 4; ++bx) {
+          const int c = bx * 32;                          // column inside the half
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bs[c + j];
+          const int col0 = n0 + half * 128 + c;
+          if (tail_tile) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j >= g.N) f[j] = -INFINITY;
+          }
+          float t[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t[j] = fmaxf(f[j], f[j + 16]);
+#pragma unroll
+          for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+            for (int j = 0; j < w; ++j) t[j] = fmaxf(t[j], t[j + w]);
+          const float bm = t[0];
+          cm[bx] = bm;
+          if (!(vstat.dbg & 2)) {
+          const float nm = fmaxf(run_m, bm);
+          run_s *= ex2_approx((run_m - nm) * kLog2e);
+          run_m = nm;
+          const float nb = -nm * kLog2e;
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            acc0 += ex2_approx(fmaf(f[j], kLog2e, nb));
+            acc1 += ex2_approx(fmaf(f[j + 1], kLog2e, nb));
+          }
+          run_s += acc0 + acc1;
+          }
+          bool keep = false;
+          if (bm > thr && !(vstat.dbg & 1)) {
+            if (vstat.topk > 0) {
+              // sorted insert (descending; an equal earlier chunk stays ahead), then refresh the threshold
+#pragma unroll
+              for (int j = KS - 1; j > 0; --j) top[j] = (bm > top[j - 1]) ? top[j - 1] : ((bm > top[j]) ? bm : top[j]);
+              top[0] = (bm > top[0]) ? bm : top[0];
+              thr = top[0];
+#pragma unroll
+              for (int j = 1; j < KS; ++j)
+                if (j < vstat.topk) thr = top[j];
+            }
+            keep = row < g.M;
+          }
+          // Kept chunks leave through the warp's shared-memory slots so that the warp can write them as full
+          // 128-byte lines (8 lanes per row, 4 rows per instruction).  Row-per-thread st.global.v4 touches 32
+          // lines per instruction, and a per-lane cp.async.bulk is serialised lane by lane (uniform-register
+          // operands): both cost ~36 us per step at the MSVD shape.
+          const unsigned km = __ballot_sync(0xffffffffu, keep);
+          if (km != 0u) {
+            if (keep) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts128(slot + 16u * j, __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                       __float_as_uint(f[4 * j + 3]));
+            }
+            __syncwarp();
+            const int piece = lane & 7, sub = lane >> 3;
+            const int gcol = col0 + piece * 4;
+            float* dst0 = vstat.logits + (size_t)(m0 + q * 32) * vstat.ld + gcol;
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) {
+              const int rr = i8 * 4 + sub;
+              if (((km >> rr) & 1u) && gcol < g.N) {
+                uint32_t x0, x1, x2, x3;
+                lds128(wslot + (uint32_t)rr * 144u + (uint32_t)piece * 16u, x0, x1, x2, x3);
+                *reinterpret_cast<uint4*>(dst0 + (size_t)rr * vstat.ld) = make_uint4(x0, x1, x2, x3);
+              }
+            }
+            __syncwarp();
+          }
+        }
+        tc_fence_before();
+        mbar_arrive_cta(smem_u32(&tmem_empty[a]));
+        if (row < g.M && !(vstat.dbg & 4)) {
+          *reinterpret_cast<float4*>(vstat.cmax + (size_t)row * vstat.nc + tn * 8 + half * 4) =
+              make_float4(cm[0], cm[1], cm[2], cm[3]);
+          vstat.part[(size_t)row * vstat.np + tn * 2 + half] = make_float2(run_m, run_s);
+        }
       }
-      if (EPI == EPI_LSTM) mbar_wait(smem_u32(&c_full), (uint32_t)(it & 1));
-      mbar_wait(smem_u32(&tmem_full[a]), (uint32_t)((it >> 1) & 1));
-      tc_fence_after();
-      epi_bar_sync();                                  // bias staged by all
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
-
-      if (EPI == EPI_STORE) {
-        constexpr int kColsPerBox = 128 / (int)sizeof(OutT);
-        constexpr int kLdPerBox = kColsPerBox / 32;
-        constexpr int kBoxes = BN / kColsPerBox;
+    } else if (EPI == EPI_STORE) {
+      // warps 2..5 = column half 0, warps 6..9 = column half 1 (each group covers the four lane quarters)
+      const int half = (warp - 2) >> 2;
+      const int eh = ((warp - 2) & 3) * 32 + lane;        // 0..127 inside the half
+      const int bar_id = 1 + half;
+      constexpr int kColsPerBox = 128 / (int)sizeof(OutT);
+      constexpr int kLdPerBox = kColsPerBox / 32;
+      constexpr int kBoxesPerHalf = (BN / 2) / kColsPerBox;   // 4 (fp32) or 2 (16-bit outputs)
+      const uint32_t box_base = smem_u32(io_smem) + (uint32_t)(half * 2) * kBoxBytes;
+      for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        const int a = it & 1;
+        float* bs = bias_s[a] + half * 128;
+        {
+          const int col = n0 + half * 128 + eh;
+          bs[eh] = (g.bias[0] != nullptr && col < g.N) ? g.bias[0][col] : 0.f;
+        }
+        mbar_wait(smem_u32(&tmem_full[a]), (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // bias of this half staged
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + half * 128);
 #pragma unroll 1
-        for (int bx = 0; bx < kBoxes; ++bx) {
-          const uint32_t box = smem_u32(io_smem) + (uint32_t)(bx & 1) * kBoxBytes;
+        for (int bx = 0; bx < kBoxesPerHalf; ++bx) {
+          const uint32_t box = box_base + (uint32_t)(bx & 1) * kBoxBytes;
           // the staging box written two boxes ago must have been read by its store
-          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          epi_bar_sync();
+          if (eh == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
           for (int h = 0; h < kLdPerBox; ++h) {
-            const int c = bx * kColsPerBox + h * 32;
+            const int c = bx * kColsPerBox + h * 32;     // column inside the half
             uint32_t v[32];
             tmem_ld32(taddr + (uint32_t)c, v);
             tmem_ld_wait();
@@ -559,19 +726,35 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
                        pack16<OutT>(f[8 * j + 4], f[8 * j + 5]), pack16<OutT>(f[8 * j + 6], f[8 * j + 7]));
             }
           }
-          if (bx == kBoxes - 1) {                       // all TMEM reads of this accumulator are done
+          if (bx == kBoxesPerHalf - 1) {                  // all TMEM reads of this accumulator half are done
             tc_fence_before();
             mbar_arrive_cta(smem_u32(&tmem_empty[a]));
           }
           fence_proxy_async_smem();
-          epi_bar_sync();
-          if (et == 0) {
-            const int col = n0 + bx * kColsPerBox;
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (eh == 0) {
+            const int col = n0 + half * 128 + bx * kColsPerBox;
             if (col < g.N) tma_store_2d(&maps.io[0], box, g.io_col0[0][0] + col, m0);
             tma_store_commit();
           }
         }
-      } else {
+      }
+      if (eh == 0) tma_store_wait_read();
+    } else {
+      const int et = threadIdx.x - 64;
+      for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        const int a = it & 1;
+        float* bs = bias_s[a];
+        for (int i = et; i < BN; i += 128) {
+          const int col = n0 + i;
+          bs[i] = (g.bias[0] != nullptr && col < g.N) ? g.bias[0][col] : 0.f;
+        }
+        mbar_wait(smem_u32(&c_full), (uint32_t)(it & 1));
+        mbar_wait(smem_u32(&tmem_full[a]), (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        epi_bar_sync();                                  // bias staged by all
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
         const uint32_t c_s = smem_u32(io_smem);
         const uint32_t h_box = smem_u32(io_smem + 2 * kBoxBytes);
 #pragma unroll 1
@@ -618,7 +801,6 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         epi_bar_sync();                                 // nobody rewrites h_box before the stores have read it
       }
     }
-    if (et == 0) tma_store_wait_read();
   }
   tc_fence_before();
   __syncthreads();
@@ -863,27 +1045,50 @@ int launch_direct(const GemmArgs& g, int64_t a_cols, const Epi& epi, cudaStream_
 }
 
 // ---- plain store (+bias, +tanh)
+// `stats` (fp32 output only): also emit the per-row chunk maxima / log-sum-exp partials described at
+// VocabStats; forces the persistent kernel.  Caller guarantees N >= 256 and the buffers' nc/np match.
 template <class OutT, bool TANH>
-int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH, false>& e, cudaStream_t stream) {
+int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH, false>& e, cudaStream_t stream,
+                   const VocabStats* stats = nullptr) {
   if (g.M == 0 || g.N == 0) return VC_OK;
-  if (e.C2[0] != nullptr || g.nz != 1 || !tma_ok(e.C[0], e.ldc, sizeof(OutT))) return launch_direct(g, a_cols, e, stream);
+  const bool direct = e.C2[0] != nullptr || g.nz != 1 || !tma_ok(e.C[0], e.ldc, sizeof(OutT));
+  if (stats != nullptr) VC_CHECK(!direct && sizeof(OutT) == 4 && !TANH && g.N >= 256, "vocab statistics need a TMA-storable fp32 output");
+  if (direct) return launch_direct(g, a_cols, e, stream);
   TcMaps mp;
   TcArgs ta;
   const int64_t tiles256 = (int64_t)((g.M + 127) / 128) * ((g.N + 255) / 256);
-  const int BN = (g.N >= 256 && tiles256 >= 148) ? 256 : 128;
+  const int BN = (stats != nullptr || (g.N >= 256 && tiles256 >= 148)) ? 256 : 128;
   VC_TRY(fill_ab(mp, ta, g, a_cols, BN));
   ta.bias[0] = ta.bias[1] = e.bias[0];
   VC_TRY(get_map(&mp.io[0], e.C[0], (uint64_t)g.M, (uint64_t)g.N, (uint64_t)e.ldc, BM, sizeof(OutT)));
   if (BN == 256) {
     // persistent, TMEM double-buffered: one CTA per SM loops over the tiles
-    // (4 stages + staging + static smem would exceed the 227 KB limit by 128 bytes)
+    // (4 stages + staging + static smem would exceed the 227 KB limit)
     constexpr int kStages = 3;
-    const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 2 * kBoxBytes + 1024;
-    auto kern = gemm_tc_persistent_kernel<kStages, EPI_STORE, OutT, TANH>;
-    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 4 * kBoxBytes + 1024;
     const int tm = (g.M + BM - 1) / BM, tn = (g.N + 255) / 256;
     const int ctas = tm * tn < num_sms() ? tm * tn : num_sms();
-    kern<<<ctas, kThreads, smem, stream>>>(mp, ta, tm, tn);
+    VocabStats vs;
+    memset(&vs, 0, sizeof(vs));
+    if constexpr (sizeof(OutT) == 4 && !TANH) {
+      if (stats != nullptr) {
+        vs = *stats;
+        VC_CHECK(vs.nc == 8 * tn && vs.np == 2 * tn, "vocab statistics buffers do not match the tiling (nc=%d np=%d tn=%d)", vs.nc, vs.np, tn);
+        vs.logits = e.C[0];
+        vs.ld = e.ldc;
+        // no staging boxes: one 144-byte slot per epilogue thread for the sparse row-chunk stores
+        constexpr int kStatStages = 3;
+        const size_t smem_st = (size_t)kStatStages * (BM * BK * 2 + 256 * BK * 2) + 256 * 144 + 1024;
+        auto kern = gemm_tc_persistent_kernel<kStatStages, EPI_STORE, OutT, TANH, true>;
+        VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st));
+        kern<<<ctas, PersistentCfg<EPI_STORE>::kThreads, smem_st, stream>>>(mp, ta, tm, tn, vs);
+        VC_CUDA(cudaGetLastError());
+        return VC_OK;
+      }
+    }
+    auto kern = gemm_tc_persistent_kernel<kStages, EPI_STORE, OutT, TANH, false>;
+    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<ctas, PersistentCfg<EPI_STORE>::kThreads, smem, stream>>>(mp, ta, tm, tn, vs);
   } else {
     // 3 stages x 32 KB: two CTAs co-reside per SM, so one CTA's epilogue overlaps the other's main loop
     constexpr int kStages = 3;
@@ -930,9 +1135,11 @@ inline int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiLstm<bf16,
   if (!has_add && g.nz == 1 && (int)(grid.x * grid.y) >= num_sms()) {
     constexpr int kStages = 3;
     const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 3 * kBoxBytes + 1024;
-    auto kern = gemm_tc_persistent_kernel<kStages, EPI_LSTM, bf16, false>;
+    auto kern = gemm_tc_persistent_kernel<kStages, EPI_LSTM, bf16, false, false>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<num_sms(), kThreads, smem, stream>>>(mp, ta, (int)grid.y, (int)grid.x);
+    VocabStats vs;
+    memset(&vs, 0, sizeof(vs));
+    kern<<<num_sms(), PersistentCfg<EPI_LSTM>::kThreads, smem, stream>>>(mp, ta, (int)grid.y, (int)grid.x, vs);
     VC_CUDA(cudaGetLastError());
     return VC_OK;
   }
