@@ -106,3 +106,16 @@ def test_gather_captions_gloo_world2():
     exp_t = [[10, 10, 10, 10, 1]] * 3 + [[11] * 5] * 2
     for _, t, l in res:
         assert t == exp_t and l == [4, 4, 4, 5, 5]
+
+
+def test_host_chunk_schedule_covers_batch():
+    """The host-feature pipeline's chunk schedule (video_captioning_model._host_spans): contiguous cover of
+    [0, B) with no chunk above the staging size."""
+    import video_captioning_b200 as vc
+    spans_of = vc.VideoCaptioningModel._host_spans
+    for B in (1, 7, 31, 128, 129, 255, 256, 257, 1000, 1024, 4096):
+        for chunk in (1, 8, 64, 256):
+            sp = spans_of(B, chunk)
+            assert sp[0][0] == 0 and sp[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(sp, sp[1:]))
+            assert all(0 < hi - lo <= chunk for lo, hi in sp)

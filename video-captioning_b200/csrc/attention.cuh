@@ -21,6 +21,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -352,6 +354,499 @@ __global__ void __launch_bounds__(kAttnThreads) attn_step_kernel(const AttnArgs<
         }
     }
   }
+}
+
+// ---------------------------------------------------------------- additive attention, bf16 mode (v3)
+// The Bahdanau / Luong-concat step of the benchmark configuration.  R*T*A tanh per step make it MUFU-bound
+// (16 tanh/clk/SM; tanh.approx.f16x2 retires 2 results per lane but at half the instruction rate), so
+// the kernel is built to keep the XU pipe fed: small CTAs (one video, 4 warps, <= 64 registers, ~6 KB smem)
+// so that 8 CTAs per SM -- every video of a 1024-video step at once -- interleave their MUFU-heavy scoring
+// with the FFMA-heavy context phase of their neighbours.
+//   queries  fp16 [R, D], written by the query-projection GEMM's epilogue; every lane keeps its 16-byte
+//            chunk of the K queries (and of v) in registers for the whole kernel -- no smem staging
+//   scoring  warp = (D half, frame slot); per frame pair: 2 LDG.128 of fp16 keys, K x 2 x 4 (HADD2, MUFU.TANH,
+//            HFMA2), fp32 butterfly (first stage folds the two frames), partial sums of the two D halves
+//            combined in the softmax phase
+//   softmax  one warp per (beam) row
+//   context  thread = 4 columns of enc_out over all frames (no cross-thread reduction), fp32 FFMA,
+//            weights read as float4 from smem
+struct AttnAddArgs {
+  const __half* keys;    // [B, T, D] fp16 projected keys (attention.py:52 / :140)
+  const __half* q;       // [R, D] fp16 projected queries incl. bias (attention.py:53 / :138)
+  const __half* v;       // [D] fp16 score vector (attention.py:28 / :99)
+  float v_bias;
+  const bf16* values;    // [B, T, H] enc_out
+  const float* mask;     // [B, T] or nullptr
+  bf16* ctx;             // [R, ctx_ld]
+  int64_t ctx_ld;
+  float* attn_out;       // optional [R, attn_ld]
+  int64_t attn_ld;
+  int B, T, D, H;
+  // Scoring gate: at most `sem_limit` CTAs per SM are in the MUFU-bound scoring phase at a time (counter per SM
+  // in global memory, zero before and after every launch).  All CTAs of a step are resident at once; without the
+  // gate they run scoring together (XU saturated, stretched 7x) and then the context phase together (XU idle).
+  // With it a CTA scores at nearly full XU rate and its FFMA/memory-bound context phase overlaps the scoring of
+  // the next CTAs.  nullptr: no gate.
+  int* sm_sem;
+  int sem_limit;
+};
+
+constexpr int kAddThreads = 128;
+
+// 4 half2 words of (key + q) -> tanh -> * v, accumulated in one half2
+__device__ __forceinline__ __half2 additive4_h2(const uint4& key, const uint4& q, const uint4& v) {
+  const uint32_t kw[4] = {key.x, key.y, key.z, key.w};
+  const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+  const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+  __half2 acc = __float2half2_rn(0.f);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    __half2 x = __hadd2(*reinterpret_cast<const __half2*>(&kw[p]), *reinterpret_cast<const __half2*>(&qw[p]));
+    uint32_t xi = *reinterpret_cast<uint32_t*>(&x), yi;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(yi) : "r"(xi));
+    acc = __hfma2(*reinterpret_cast<const __half2*>(&vw[p]), *reinterpret_cast<__half2*>(&yi), acc);
+  }
+  return acc;
+}
+__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// K: exact beam count; DH: warps sharing one frame (2: D in (256, 512], 1: D <= 256)
+template <int K, int DH>
+__global__ void __launch_bounds__(kAddThreads, 7) attn_additive_kernel(const AttnAddArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int T = a.T, D = a.D, H = a.H;
+  const int Tp = (T + 3) & ~3;                   // weights padded to a multiple of 4 frames (zeros)
+  float* part = smem;                            // [DH][K][Tp] partial scores
+  float* wgt = smem + DH * K * Tp;               // [K][Tp] softmax weights
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NFS = 4 / DH;                    // frame slots
+  const int dh = (DH == 2) ? (warp & 1) : 0;
+  const int fs = (DH == 2) ? (warp >> 1) : warp;
+
+  // ---- scores
+  int* sem = nullptr;
+  {
+    const int d0 = (dh * 32 + lane) * 8;
+    const bool live = d0 < D;
+    uint4 qreg[K];
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int k = 0; k < K; ++k) qreg[k] = live ? ldg128(a.q + ((int64_t)b * K + k) * D + d0) : zero4;
+    const uint4 vreg = live ? ldg128(a.v + d0) : zero4;           // v = 0: dead lanes contribute nothing
+    const __half* kp = a.keys + (int64_t)b * T * D + d0;
+    float* prow = part + dh * K * Tp;
+    // software pipeline: the next frame pair's keys are in flight while this pair's tanh work runs
+    uint4 key0 = (live && fs < T) ? ldg128(kp + (int64_t)fs * D) : zero4;
+    uint4 key1 = (live && fs + NFS < T) ? ldg128(kp + (int64_t)(fs + NFS) * D) : zero4;
+    if (a.sm_sem != nullptr) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      sem = a.sm_sem + smid;
+      if (tid == 0) {
+        while (atomicAdd(sem, 1) >= a.sem_limit) {
+          atomicSub(sem, 1);
+          __nanosleep(400);
+        }
+      }
+      __syncthreads();
+    }
+    for (int t = fs; t < T; t += 2 * NFS) {
+      const int t1 = t + NFS;
+      const int tn0 = t + 2 * NFS, tn1 = t1 + 2 * NFS;
+      const uint4 nxt0 = (live && tn0 < T) ? ldg128(kp + (int64_t)tn0 * D) : zero4;
+      const uint4 nxt1 = (live && tn1 < T) ? ldg128(kp + (int64_t)tn1 * D) : zero4;
+      float s0[K], s1[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float2 f0 = __half22float2(additive4_h2(key0, qreg[k], vreg));
+        const float2 f1 = __half22float2(additive4_h2(key1, qreg[k], vreg));
+        s0[k] = f0.x + f0.y;
+        s1[k] = f1.x + f1.y;
+      }
+      // butterfly: the xor-16 stage folds the two frames (lanes 0-15 end up with frame t, lanes 16-31 with t1)
+      const bool hi = (lane & 16) != 0;
+      float s[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float send = hi ? s0[k] : s1[k];
+        const float keep = hi ? s1[k] : s0[k];
+        s[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < K; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+      if ((lane & 15) == 0) {
+        const int tt = hi ? t1 : t;
+        if (tt < T) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) prow[k * Tp + tt] = s[k];
+        }
+      }
+      key0 = nxt0;
+      key1 = nxt1;
+    }
+  }
+  __syncthreads();
+  if (sem != nullptr && tid == 0) atomicSub(sem, 1);
+
+  // ---- masked softmax over T, one warp per beam row (attention.py:61-64)
+  for (int k = warp; k < K; k += kAddThreads / 32) {
+    float m = -INFINITY;
+    for (int t = lane; t < T; t += 32) {
+      float x = part[k * Tp + t] + a.v_bias;
+      if (DH == 2) x += part[(K + k) * Tp + t];
+      if (a.mask != nullptr && a.mask[(int64_t)b * T + t] == 0.f) x = -1e9f;
+      wgt[k * Tp + t] = x;
+      m = fmaxf(m, x);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float e = __expf(wgt[k * Tp + t] - m);
+      wgt[k * Tp + t] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int t = lane; t < Tp; t += 32) {
+      const float w = (t < T) ? wgt[k * Tp + t] * inv : 0.f;
+      wgt[k * Tp + t] = w;
+      if (a.attn_out != nullptr && t < T) a.attn_out[((int64_t)b * K + k) * a.attn_ld + t] = w;
+    }
+  }
+  __syncthreads();
+
+  // ---- context = sum_t w[k][t] * enc[t][:]  (attention.py:68-71): 4 columns per thread, all frames
+  const bf16* vv = a.values + (int64_t)b * T * H;
+  for (int c0 = tid * 4; c0 < H; c0 += kAddThreads * 4) {
+    float acc[K][4];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+    constexpr int FB = 8;                          // frames per batch: 8 independent 8-byte loads in flight per thread
+    for (int t = 0; t < Tp; t += FB) {
+      uint2 e[FB];
+#pragma unroll
+      for (int f = 0; f < FB; ++f)
+        e[f] = (t + f < T) ? __ldg(reinterpret_cast<const uint2*>(vv + (int64_t)(t + f) * H + c0)) : make_uint2(0u, 0u);
+#pragma unroll
+      for (int g4 = 0; g4 < FB / 4; ++g4) {
+        if (t + 4 * g4 < Tp) {
+          float4 w4[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) w4[k] = *reinterpret_cast<const float4*>(wgt + k * Tp + t + 4 * g4);
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const uint2 ee = e[4 * g4 + f];
+            const float x0 = __uint_as_float(ee.x << 16), x1 = __uint_as_float(ee.x & 0xffff0000u);
+            const float x2 = __uint_as_float(ee.y << 16), x3 = __uint_as_float(ee.y & 0xffff0000u);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              const float w = (f == 0) ? w4[k].x : (f == 1) ? w4[k].y : (f == 2) ? w4[k].z : w4[k].w;
+              acc[k][0] = fmaf(w, x0, acc[k][0]);
+              acc[k][1] = fmaf(w, x1, acc[k][1]);
+              acc[k][2] = fmaf(w, x2, acc[k][2]);
+              acc[k][3] = fmaf(w, x3, acc[k][3]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) store4(a.ctx + ((int64_t)b * K + k) * a.ctx_ld + c0, acc[k]);
+  }
+}
+
+// ---------------------------------------------------------------- additive attention, bf16 mode (v4: tensor-core reductions)
+// v3 above is bound by instruction issue (4.9 instructions per tanh: packed add, 2 MUFU, pack, packed fma,
+// fp16->fp32 conversions and a 5-stage shuffle butterfly per frame and beam), not yet by the XU pipe.  Here both
+// reductions of the step run on the tensor cores through mma.sync (register fragments, no shared-memory operands):
+//   scores   s[t,k] = sum_j v[j] * tanh(key[t,j] + q[k,j]).  A 16x16 A fragment holds tanh values for 16 frames x
+//            16 features, B is v replicated over the 8 columns, the fp32 accumulator tile carries the running dot
+//            product over all feature blocks: lane (g, tg) evaluates frames g / g+8 on the 8 features of its tg --
+//            the dot product does not care how features are permuted as long as key, q and v agree, so every lane's
+//            8 features are one contiguous 16-byte chunk.  2.2 instructions per tanh; no shuffles, no conversions.
+//   context  ctx^T[col, k] = sum_t enc[t, col] * w[k, t]: A = enc^T (ldmatrix.trans from a staged 16-frame tile),
+//            B = softmax weights split into bf16 hi + lo parts (two MMAs: fp32-grade weights), 8 m-tiles per warp.
+// Warps split the feature dimension for the scores (partials summed in the softmax) and the columns for the context.
+constexpr int kMmaThreads = 128;
+constexpr int kEncPad = 8;   // bf16 elements of row padding in the staged enc tile (ldmatrix rows hit distinct banks)
+
+__device__ __forceinline__ uint32_t tanh_h2(uint32_t key, uint32_t q) {
+  __half2 x = __hadd2(*reinterpret_cast<const __half2*>(&key), *reinterpret_cast<const __half2*>(&q));
+  uint32_t xi = *reinterpret_cast<uint32_t*>(&x), yi;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(yi) : "r"(xi));
+  return yi;
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// split two fp32 weights into packed bf16 hi and lo parts (hi + lo reproduces ~16 mantissa bits)
+__device__ __forceinline__ void split_bf16x2(float w0, float w1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+  const __nv_bfloat162 h = __halves2bfloat162(h0, h1);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(w0 - __bfloat162float(h0), w1 - __bfloat162float(h1));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// K: exact beam count (<= 8).  Requires D % 32 == 0, H % 64 == 0.
+template <int K, int NBUF, int MINB>
+__global__ void __launch_bounds__(kMmaThreads, MINB) attn_additive_mma_kernel(const AttnAddArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_u8[];
+  const int T = a.T, D = a.D, H = a.H;
+  const int NT = (T + 15) >> 4;                  // 16-frame tiles
+  const int Tp = NT * 16;
+  const int pitch = H + kEncPad;                 // staged enc row pitch (elements)
+  __half* q_s = reinterpret_cast<__half*>(smem_u8);                        // [K][D]
+  __half* v_s = q_s + K * D;                                               // [D]
+  float* part = reinterpret_cast<float*>(v_s + D);                         // [4][K][Tp]
+  float* wgt = part + 4 * K * Tp;                                          // [K][Tp]
+  bf16* enc_s = reinterpret_cast<bf16*>(wgt + K * Tp);                     // [2][16][pitch]; later [K][H] output staging
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const bf16* vv = a.values + (int64_t)b * T * H;
+
+  // stage one 16-frame tile of enc_out (frames past T are clamped; their weights are zero)
+  auto stage_enc = [&](int ks, int buf) {
+    const int chunks_per_row = H / 8;            // 16-byte chunks
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(enc_s + (size_t)buf * 16 * pitch);
+    for (int rr = 0; rr < 16; ++rr) {            // (no integer division: it would run on the XU pipe the tanh needs)
+      int t = ks * 16 + rr;
+      t = t < T ? t : T - 1;
+      for (int cc = tid; cc < chunks_per_row; cc += kMmaThreads)
+        cp_async16(base + (uint32_t)(rr * pitch + cc * 8) * 2u, vv + (int64_t)t * H + cc * 8);
+    }
+    cp_async_commit();
+  };
+  stage_enc(0, 0);                               // lands during the scoring phase
+
+  // queries + score vector -> shared memory (fp16)
+  for (int i = tid; i < K * D / 8; i += kMmaThreads)
+    reinterpret_cast<uint4*>(q_s)[i] = ldg128(a.q + (int64_t)b * K * D + (int64_t)i * 8);
+  for (int i = tid; i < D / 8; i += kMmaThreads) reinterpret_cast<uint4*>(v_s)[i] = ldg128(a.v + (int64_t)i * 8);
+  __syncthreads();
+
+  // ---- scores: warp w owns feature blocks fb = w, w+4, ... (32 features each)
+  {
+    const int nfb = D / 32;
+    const __half* kbase = a.keys + (int64_t)b * T * D;
+    for (int ft = 0; ft < NT; ++ft) {
+      int t0 = ft * 16 + g, t1 = t0 + 8;
+      const int tc0 = t0 < T ? t0 : T - 1, tc1 = t1 < T ? t1 : T - 1;
+      const __half* k0p = kbase + (int64_t)tc0 * D + tg * 8;
+      const __half* k1p = kbase + (int64_t)tc1 * D + tg * 8;
+      float acc[K][4];
+#pragma unroll
+      for (int k = 0; k < K; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
+      uint4 key0 = make_uint4(0u, 0u, 0u, 0u), key1 = key0;
+      if (warp < nfb) { key0 = ldg128(k0p + warp * 32); key1 = ldg128(k1p + warp * 32); }
+      for (int fb = warp; fb < nfb; fb += 4) {
+        const int feat = fb * 32 + tg * 8;
+        uint4 nx0 = make_uint4(0u, 0u, 0u, 0u), nx1 = nx0;
+        if (fb + 4 < nfb) { nx0 = ldg128(k0p + (fb + 4) * 32); nx1 = ldg128(k1p + (fb + 4) * 32); }
+        const uint4 v4 = *reinterpret_cast<const uint4*>(v_s + feat);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const uint4 q4 = *reinterpret_cast<const uint4*>(q_s + k * D + feat);
+          mma_f16(acc[k], tanh_h2(key0.x, q4.x), tanh_h2(key1.x, q4.x), tanh_h2(key0.y, q4.y), tanh_h2(key1.y, q4.y), v4.x, v4.y);
+          mma_f16(acc[k], tanh_h2(key0.z, q4.z), tanh_h2(key1.z, q4.z), tanh_h2(key0.w, q4.w), tanh_h2(key1.w, q4.w), v4.z, v4.w);
+        }
+        key0 = nx0;
+        key1 = nx1;
+      }
+      if (tg == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          part[(warp * K + k) * Tp + t0] = acc[k][0];     // every column of the accumulator tile holds the dot product
+          part[(warp * K + k) * Tp + t1] = acc[k][2];
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- masked softmax over T, one warp per beam row (attention.py:61-64)
+  for (int k = warp; k < K; k += kMmaThreads / 32) {
+    float m = -INFINITY;
+    for (int t = lane; t < T; t += 32) {
+      float x = part[k * Tp + t] + part[(K + k) * Tp + t] + part[(2 * K + k) * Tp + t] + part[(3 * K + k) * Tp + t] + a.v_bias;
+      if (a.mask != nullptr && a.mask[(int64_t)b * T + t] == 0.f) x = -1e9f;
+      wgt[k * Tp + t] = x;
+      m = fmaxf(m, x);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float e = __expf(wgt[k * Tp + t] - m);
+      wgt[k * Tp + t] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int t = lane; t < Tp; t += 32) {
+      const float w = (t < T) ? wgt[k * Tp + t] * inv : 0.f;
+      wgt[k * Tp + t] = w;
+      if (a.attn_out != nullptr && t < T) a.attn_out[((int64_t)b * K + k) * a.attn_ld + t] = w;
+    }
+  }
+  // (the barrier that publishes wgt is the first one of the loop below)
+
+  // ---- context: warp w owns columns [w*H/4, (w+1)*H/4) as m-tiles of 16
+  {
+    const int cw = H / 4;                        // columns per warp
+    const int nmt = cw / 16;                     // m-tiles per warp (8 at H = 512)
+    constexpr int MAXMT = 8;
+    for (int mt0 = 0; mt0 < nmt; mt0 += MAXMT) { // one pass for H <= 512
+      float c[MAXMT][4];
+#pragma unroll
+      for (int i = 0; i < MAXMT; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
+      for (int ks = 0; ks < NT; ++ks) {
+        const int buf = (mt0 == 0 && NBUF == 2) ? (ks & 1) : 0;
+        if (mt0 == 0 && NBUF == 1) {
+          if (ks > 0) { __syncthreads(); stage_enc(ks, 0); }      // tile ks-1 consumed by everyone
+          cp_async_wait<0>();
+        } else if (mt0 == 0) {
+          if (ks + 1 < NT) { stage_enc(ks + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        } else {
+          __syncthreads();
+          stage_enc(ks, 0);
+          cp_async_wait<0>();
+        }
+        __syncthreads();                         // tile ks visible to all warps (and wgt on the first trip)
+        // B fragments: weights of beam g for frames ks*16 + {2tg, 2tg+1} and + 8, hi/lo split
+        uint32_t bh0 = 0u, bl0 = 0u, bh1 = 0u, bl1 = 0u;
+        if (g < K) {
+          const float2 w0 = *reinterpret_cast<const float2*>(wgt + g * Tp + ks * 16 + 2 * tg);
+          const float2 w1 = *reinterpret_cast<const float2*>(wgt + g * Tp + ks * 16 + 2 * tg + 8);
+          split_bf16x2(w0.x, w0.y, bh0, bl0);
+          split_bf16x2(w1.x, w1.y, bh1, bl1);
+        }
+        const uint32_t tile = (uint32_t)__cvta_generic_to_shared(enc_s + (size_t)buf * 16 * pitch);
+        // ldmatrix row address of this lane: matrix j = lane/8 -> frames (j/2)*8 + lane%8, columns + (j%2)*8
+        const int lrow = ((lane >> 4) << 3) + (lane & 7), lcol = ((lane >> 3) & 1) << 3;
+#pragma unroll
+        for (int i = 0; i < MAXMT; ++i) {
+          if (mt0 + i < nmt) {
+            const int col0 = warp * cw + (mt0 + i) * 16;
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4_trans(tile + (uint32_t)(lrow * pitch + col0 + lcol) * 2u, a0, a1, a2, a3);
+            mma_bf16(c[i], a0, a1, a2, a3, bh0, bh1);
+            mma_bf16(c[i], a0, a1, a2, a3, bl0, bl1);
+          }
+        }
+        if (mt0 == 0 && NBUF == 2 && ks + 1 < NT) __syncthreads();   // everyone done with buf before it is refilled two trips later
+      }
+      // c[i] = {ctx[col0+g][2tg], ctx[col0+g][2tg+1], ctx[col0+g+8][2tg], ctx[col0+g+8][2tg+1]} (col, beam)
+      __syncthreads();                           // all tiles consumed: reuse enc_s as [K][H] bf16 output staging
+      bf16* out_s = enc_s;
+#pragma unroll
+      for (int i = 0; i < MAXMT; ++i) {
+        if (mt0 + i < nmt) {
+          const int col0 = warp * cw + (mt0 + i) * 16;
+          const int k0 = 2 * tg, k1 = 2 * tg + 1;
+          if (k0 < K) { out_s[k0 * H + col0 + g] = __float2bfloat16_rn(c[i][0]); out_s[k0 * H + col0 + g + 8] = __float2bfloat16_rn(c[i][2]); }
+          if (k1 < K) { out_s[k1 * H + col0 + g] = __float2bfloat16_rn(c[i][1]); out_s[k1 * H + col0 + g + 8] = __float2bfloat16_rn(c[i][3]); }
+        }
+      }
+      __syncthreads();
+      if (mt0 + MAXMT >= nmt) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          for (int c8 = tid * 8; c8 < H; c8 += kMmaThreads * 8)
+            *reinterpret_cast<uint4*>(a.ctx + ((int64_t)b * K + k) * a.ctx_ld + c8) = *reinterpret_cast<const uint4*>(out_s + k * H + c8);
+      }
+    }
+  }
+}
+
+inline int attn_mma_nbuf() {           // VC_ATTN_NBUF=2: double-buffered enc staging, 4 CTAs/SM; 1 (default): single buffer, 7 CTAs/SM
+  static int n = 0;
+  if (n == 0) { const char* e = getenv("VC_ATTN_NBUF"); n = (e != nullptr && e[0] == '2') ? 2 : 1; }
+  return n;
+}
+inline bool attn_additive_mma_ok(int K, int D, int H, int T) {
+  const int Tp = (T + 15) & ~15;
+  const size_t smem = (size_t)(K + 1) * D * 2 + (size_t)5 * K * Tp * 4 + (size_t)attn_mma_nbuf() * 16 * (H + kEncPad) * 2;
+  return K >= 1 && K <= 8 && D % 32 == 0 && H % 64 == 0 && H <= 512 && smem <= 56 * 1024;
+}
+
+inline int launch_attn_additive_mma(const AttnAddArgs& a, int K, cudaStream_t stream) {
+  VC_CHECK(attn_additive_mma_ok(K, a.D, a.H, a.T), "additive attention (mma): K=%d D=%d H=%d T=%d not supported", K, a.D, a.H, a.T);
+  VC_CHECK(a.ctx_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ctx) & 15) == 0, "additive attention (mma): ctx must be 16-byte aligned");
+  const int Tp = (a.T + 15) & ~15;
+  const int nbuf = attn_mma_nbuf();
+  const size_t smem = (size_t)(K + 1) * a.D * 2 + (size_t)5 * K * Tp * 4 + (size_t)nbuf * 16 * (a.H + kEncPad) * 2;
+#define VC_MMA_LAUNCH(KK)                                                                                  \
+  do {                                                                                                     \
+    if (nbuf == 2) {                                                                                       \
+      auto kern = attn_additive_mma_kernel<KK, 2, 4>;                                                      \
+      VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+      kern<<<a.B, kMmaThreads, smem, stream>>>(a);                                                         \
+    } else {                                                                                               \
+      auto kern = attn_additive_mma_kernel<KK, 1, 7>;                                                      \
+      VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+      kern<<<a.B, kMmaThreads, smem, stream>>>(a);                                                         \
+    }                                                                                                      \
+  } while (0)
+  switch (K) {
+    case 1: VC_MMA_LAUNCH(1); break;
+    case 2: VC_MMA_LAUNCH(2); break;
+    case 3: VC_MMA_LAUNCH(3); break;
+    case 4: VC_MMA_LAUNCH(4); break;
+    case 5: VC_MMA_LAUNCH(5); break;
+    case 6: VC_MMA_LAUNCH(6); break;
+    case 7: VC_MMA_LAUNCH(7); break;
+    default: VC_MMA_LAUNCH(8); break;
+  }
+#undef VC_MMA_LAUNCH
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+inline bool attn_additive_fast_ok(int K, int D, int H) {
+  return (K == 1 || K == 3 || K == 5) && D % 8 == 0 && D <= 512 && H % 4 == 0;
+}
+
+inline int launch_attn_additive(const AttnAddArgs& a, int K, cudaStream_t stream) {
+  VC_CHECK(attn_additive_fast_ok(K, a.D, a.H), "additive attention fast path: K=%d D=%d H=%d not supported", K, a.D, a.H);
+  const int DH = a.D > 256 ? 2 : 1;
+  const int Tp = (a.T + 3) & ~3;
+  const size_t smem = sizeof(float) * (size_t)(DH + 1) * K * Tp;
+  VC_CHECK(smem <= 48 * 1024, "additive attention: K=%d T=%d needs %zu B shared memory", K, a.T, smem);
+#define VC_ADD_LAUNCH(KK, DD) attn_additive_kernel<KK, DD><<<a.B, kAddThreads, smem, stream>>>(a)
+  if (DH == 2) {
+    if (K == 1) VC_ADD_LAUNCH(1, 2);
+    else if (K == 3) VC_ADD_LAUNCH(3, 2);
+    else VC_ADD_LAUNCH(5, 2);
+  } else {
+    if (K == 1) VC_ADD_LAUNCH(1, 1);
+    else if (K == 3) VC_ADD_LAUNCH(3, 1);
+    else VC_ADD_LAUNCH(5, 1);
+  }
+#undef VC_ADD_LAUNCH
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
 }
 
 // KT: element type of a.skeys (see AttnArgs)

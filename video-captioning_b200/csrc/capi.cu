@@ -126,6 +126,10 @@ struct vc_model {
   void* Wval = nullptr; float* bval = nullptr;
   void* Wq = nullptr; float* bq = nullptr;
   float* vvec = nullptr; float vbias = 0.f;
+  __half* vvec_h = nullptr;               // fp16 copy of vvec (bf16 mode, additive attention fast path)
+  int attn_gate = 0;                      // VC_ATTN_GATE: CTAs per SM allowed in the v3 scoring phase at a time (0 = no gate; measured: no gain)
+  int attn_variant = 4;                   // VC_ATTN_VARIANT: 4 = tensor-core reductions (default), 3 = shuffle-reduction kernel
+  bool disable_attn_v3 = false;           // VC_DISABLE_ATTN_V3=1: generic attention kernel for the additive form (A/B testing)
   void* Wao = nullptr; float* bao = nullptr;
   void* dec_W[4] = {}; float* dec_bias[4] = {};
   void* Wc = nullptr; float* bc = nullptr;
@@ -261,6 +265,11 @@ int finalize_model(vc_model* m, cudaStream_t s) {
       break;
     }
     default: set_error("unknown attention type %d", d.attention); return VC_ERR_INVALID;
+  }
+  if (m->vvec != nullptr && !std::is_same<W, float>::value) {
+    VC_TRY(dev_alloc(m, &m->vvec_h, (size_t)A));
+    cast_kernel<float, __half><<<(A + 255) / 256, 256, 0, s>>>(m->vvec, m->vvec_h, (int64_t)A);
+    VC_CUDA(cudaGetLastError());
   }
   for (int l = 0; l < d.dec_layers; ++l) {
     const int in = (l == 0) ? (E + H) : H;
@@ -576,6 +585,26 @@ int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64
   switch (d.attention) {
     case VC_ATTN_BAHDANAU:
     case VC_ATTN_LUONG_CONCAT: {
+      if constexpr (!P) {
+        const bool use_mma = m->attn_variant == 4 && attn_additive_mma_ok(K, A, H, T) && ctx_ld % 8 == 0;
+        if (!m->disable_attn_v3 && (use_mma || attn_additive_fast_ok(K, A, H))) {
+          // queries leave the projection GEMM as fp16 and are consumed from registers by the v3 kernel
+          __half* q16 = reinterpret_cast<__half*>(w.Q);
+          {
+            VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
+            VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, A, H), hq_cols, estore<__half, false, P>(q16, A, m->bq), s)));
+          }
+          AttnAddArgs aa;
+          aa.keys = reinterpret_cast<const __half*>(w.keys); aa.q = q16; aa.v = m->vvec_h; aa.v_bias = m->vbias;
+          aa.values = w.enc_act; aa.mask = mask; aa.ctx = ctx; aa.ctx_ld = ctx_ld; aa.attn_out = attn_out; aa.attn_ld = attn_ld;
+          aa.B = B; aa.T = T; aa.D = A; aa.H = H;
+          aa.sm_sem = m->attn_gate > 0 ? reinterpret_cast<int*>(w.flags) + 512 : nullptr;   // zeroed by run_decode
+          aa.sem_limit = m->attn_gate;
+          VC_SCOPE(VC_CLS_ATTN_STEP);
+          if (use_mma) return launch_attn_additive_mma(aa, K, s);
+          return launch_attn_additive(aa, K, s);
+        }
+      }
       {
         VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
         VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, A, H), hq_cols, estore<float, false, P>(w.Q, A, m->bq), s)));   // attention.py:53 / :138
@@ -647,6 +676,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
   bs.scores = w.scores; bs.alive = w.alive; bs.done = w.done; bs.best_score = w.best_score; bs.best_len = w.best_len;
   bs.best_seq = w.best_seq; bs.hist[0] = w.hist[0]; bs.hist[1] = w.hist[1];
 
+  VC_CUDA(cudaMemsetAsync(w.flags + 512, 0, sizeof(unsigned int) * 512, s));   // attention scoring-gate counters (per SM)
   {
     VC_SCOPE(VC_CLS_MISC);
     decode_init_kernel<ActT><<<R, 128, 0, s>>>(st, w.final_f32, R, K, p.start_token_id,
@@ -781,6 +811,7 @@ int attention_step_impl(vc_model_t* m, const float* enc_out, const float* hidden
   cast_kernel<float, ActT><<<256, 256, 0, s>>>(hidden, w.Hn[0], (int64_t)R * H);
   VC_CUDA(cudaGetLastError());
   VC_TRY((run_precompute<ActT>(m, w, B, T, s)));
+  VC_CUDA(cudaMemsetAsync(w.flags + 512, 0, sizeof(unsigned int) * 512, s));
   VC_TRY((run_attention<ActT>(m, w, w.Hn[0], H, H, mask, B, T, K, w.O, H, weights, T, s)));
   cast_kernel<ActT, float><<<256, 256, 0, s>>>(w.O, context, (int64_t)R * H);
   VC_CUDA(cudaGetLastError());
@@ -844,6 +875,12 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   cudaGetLastError();   // creating a handle must also work where no device is visible (CPU-side tests)
   const char* env = getenv("VC_DISABLE_PERSISTENT_LSTM");
   m->disable_persistent_lstm = env != nullptr && env[0] == '1';
+  env = getenv("VC_ATTN_VARIANT");
+  if (env != nullptr) m->attn_variant = atoi(env);
+  env = getenv("VC_ATTN_GATE");
+  if (env != nullptr) m->attn_gate = atoi(env);
+  env = getenv("VC_DISABLE_ATTN_V3");
+  m->disable_attn_v3 = env != nullptr && env[0] == '1';
   env = getenv("VC_DEBUG_VOCAB");
   m->dbg_vocab = env != nullptr ? atoi(env) : 0;
   env = getenv("VC_DISABLE_FUSED_SELECT");
