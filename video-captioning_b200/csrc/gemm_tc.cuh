@@ -439,6 +439,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// packed fp32 pairs (FADD2 / FFMA2 on sm_100): half the issue slots of the scalar forms
+__device__ __forceinline__ uint64_t pack_f2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t add_f2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma_f2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 template <int EPI> struct PersistentCfg {
   static constexpr int kEpiWarps = (EPI == EPI_STORE) ? 8 : 4;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
@@ -588,15 +606,21 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         const int row = m0 + r;
         float run_m = -1e30f, run_s = 0.f;                // online (max, sum 2^((x-max) log2e)) of this half tile
         float cm[4];
+        // TMEM loads are software-pipelined: the load of chunk bx+1 is in flight while chunk bx is processed
+        uint32_t vbuf[2][32];
+        tmem_ld32(taddr, vbuf[0]);
 #pragma unroll
         for (int bx = 0; bx < 4; ++bx) {
           const int c = bx * 32;                          // column inside the half
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)c, v);
           tmem_ld_wait();
+          if (bx + 1 < 4) tmem_ld32(taddr + (uint32_t)(c + 32), vbuf[(bx + 1) & 1]);
+          const uint32_t(&v)[32] = vbuf[bx & 1];
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bs[c + j];
+          for (int j = 0; j < 32; j += 2) {               // logits = accumulator + bias, two per FADD2
+            const uint64_t x = add_f2(pack_f2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), pack_f2(bs[c + j], bs[c + j + 1]));
+            unpack_f2(x, f[j], f[j + 1]);
+          }
           const int col0 = n0 + half * 128 + c;
           if (tail_tile) {
 #pragma unroll
@@ -613,17 +637,24 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           const float bm = t[0];
           cm[bx] = bm;
           if (!(vstat.dbg & 2)) {
-          const float nm = fmaxf(run_m, bm);
-          run_s *= ex2_approx((run_m - nm) * kLog2e);
-          run_m = nm;
-          const float nb = -nm * kLog2e;
-          float acc0 = 0.f, acc1 = 0.f;
+            const float nm = fmaxf(run_m, bm);
+            run_s *= ex2_approx((run_m - nm) * kLog2e);
+            run_m = nm;
+            const uint64_t sc2 = pack_f2(kLog2e, kLog2e), nb2 = pack_f2(-nm * kLog2e, -nm * kLog2e);
+            uint64_t e2[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            acc0 += ex2_approx(fmaf(f[j], kLog2e, nb));
-            acc1 += ex2_approx(fmaf(f[j + 1], kLog2e, nb));
-          }
-          run_s += acc0 + acc1;
+            for (int j = 0; j < 16; ++j) {
+              float y0, y1;
+              unpack_f2(fma_f2(pack_f2(f[2 * j], f[2 * j + 1]), sc2, nb2), y0, y1);
+              e2[j] = pack_f2(ex2_approx(y0), ex2_approx(y1));
+            }
+#pragma unroll
+            for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+              for (int j = 0; j < w; ++j) e2[j] = add_f2(e2[j], e2[j + w]);
+            float s0, s1;
+            unpack_f2(e2[0], s0, s1);
+            run_s += s0 + s1;
           }
           bool keep = false;
           if (bm > thr && !(vstat.dbg & 1)) {
