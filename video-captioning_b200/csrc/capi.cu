@@ -114,6 +114,7 @@ struct vc_model {
   bool finalized = false;
   int num_sms = 148;
   bool disable_persistent_lstm = false;   // VC_DISABLE_PERSISTENT_LSTM=1: per-timestep launches (A/B testing)
+  bool disable_tf32_proj = false;         // VC_DISABLE_TF32_PROJ=1: convert the features to bf16 first (A/B testing)
   int dbg_vocab = 0;                      // VC_DEBUG_VOCAB: timing experiments (gemm_tc.cuh VocabStats::dbg), results invalid
   bool disable_fused_select = false;      // VC_DISABLE_FUSED_SELECT=1: stream the whole logits row in the selection (A/B testing)
   // derived, operand-typed (float or bf16 according to d.precision)
@@ -433,15 +434,25 @@ int run_encoder(vc_model* m, WS<ActT>& w, const float* feats, int B, int T, cons
   const int F = d.feature_dim, H = d.hidden_dim;
   const int BT = B * T;
   // feature projection (:70)
-  const void* Ain = feats;
-  if (!P) {
-    VC_SCOPE(VC_CLS_CONVERT);
-    const int64_t n4 = (int64_t)BT * F / 4;
-    convert_f32_to_bf16_kernel<<<(int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16), 256, 0, s>>>(feats, w.feats_bf16, n4);
-    VC_CUDA(cudaGetLastError());
-    Ain = w.feats_bf16;
+  bool proj_done = false;
+  if constexpr (!P) {
+    // bf16 mode: the tensor cores read the fp32 features (and the fp32 weight copy) as tf32 -- no conversion pass
+    auto it = m->raw.find("encoder.feature_projection.weight");
+    if (!m->disable_tf32_proj && it != m->raw.end() && H >= 256 && F % 32 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0) {
+      VC_SCOPE(VC_CLS_ENC_FEATURE_PROJ);
+      VC_TRY(tc::launch_gemm_tc_tf32(gargs(feats, F, it->second.first, F, BT, H, F), F, estore<bf16, false, false>(w.proj, H, m->bp), s));
+      proj_done = true;
+    }
   }
-  {
+  if (!proj_done) {
+    const void* Ain = feats;
+    if (!P) {
+      VC_SCOPE(VC_CLS_CONVERT);
+      const int64_t n4 = (int64_t)BT * F / 4;
+      convert_f32_to_bf16_kernel<<<(int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16), 256, 0, s>>>(feats, w.feats_bf16, n4);
+      VC_CUDA(cudaGetLastError());
+      Ain = w.feats_bf16;
+    }
     VC_SCOPE(VC_CLS_ENC_FEATURE_PROJ);
     VC_TRY((gemm<ActT>(gargs(Ain, F, m->Wp, F, BT, H, F), F, estore<ActT, false, P>(w.proj, H, m->bp), s)));
   }
@@ -881,6 +892,8 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   if (env != nullptr) m->attn_gate = atoi(env);
   env = getenv("VC_DISABLE_ATTN_V3");
   m->disable_attn_v3 = env != nullptr && env[0] == '1';
+  env = getenv("VC_DISABLE_TF32_PROJ");
+  m->disable_tf32_proj = env != nullptr && env[0] == '1';
   env = getenv("VC_DEBUG_VOCAB");
   m->dbg_vocab = env != nullptr ? atoi(env) : 0;
   env = getenv("VC_DISABLE_FUSED_SELECT");

@@ -95,6 +95,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::tf32: fp32 operands in shared memory are read as tf32 (8 elements = 32 bytes per K step)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -128,6 +137,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN.
 __host__ __device__ constexpr uint32_t make_idesc(int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32 (format code 2), both K-major, M=128, N=BN.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int bn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 // 16-byte chunk `c` (0..7) of row `r` inside a 128B-swizzled box
@@ -462,12 +475,17 @@ template <int EPI> struct PersistentCfg {
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
 };
 
-template <int kStages, int EPI, class OutT, bool TANH, bool STATS>
+// TF32: the operands in memory are fp32 (read by the tensor cores as tf32); a k-block is still 128 bytes per row,
+// i.e. 32 elements, and one MMA covers 8 of them.  Used for the feature projection so that the fp32 input
+// features are consumed as they are (no fp32 -> bf16 conversion pass over 1.3 MB per video).
+template <int kStages, int EPI, class OutT, bool TANH, bool STATS, bool TF32 = false>
 __global__ void __launch_bounds__(PersistentCfg<EPI>::kThreads, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, const int tiles_m, const int tiles_n,
                           const VocabStats vstat) {
   static_assert(!STATS || (EPI == EPI_STORE && sizeof(OutT) == 4 && !TANH), "STATS: fp32 logits store only");
+  static_assert(!TF32 || (EPI == EPI_STORE && !STATS), "TF32 operands: plain store epilogue only");
   constexpr int BN = 256;
+  constexpr int BKE = TF32 ? 32 : BK;              // elements per k-block (128 bytes per row)
   constexpr int kEpiThreads = 32 * PersistentCfg<EPI>::kEpiWarps;
   constexpr uint32_t kABytes = BM * BK * 2;
   constexpr uint32_t kBBytes = BN * BK * 2;
@@ -483,7 +501,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const CUtensorMap* mapA = &maps.A[0];
   const CUtensorMap* mapW = &maps.W[0];
-  const int nkb = g.K / BK;
+  const int nkb = g.K / BKE;
   const int num_tiles = tiles_m * tiles_n;
   // tile schedule (m-major tile index, n fastest): round-robin, or contiguous ranges when the epilogue carries
   // per-row state from tile to tile (STATS)
@@ -523,7 +541,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, kStageBytes);
-          const int k = kb * BK;
+          const int k = kb * BKE;
           const int acol = g.a_col0[0] + k + (k >= g.a_split ? g.a_skip : 0);
           uint8_t* sa = smem + (size_t)stage * kStageBytes;
           tma_load_2d(smem_u32(sa), mapA, fb, acol, m0);
@@ -544,7 +562,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(BN);
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(BN) : make_idesc(BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
@@ -559,8 +577,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           const uint64_t da = make_smem_desc(smem_u32(sa));
           const uint64_t db = make_smem_desc(smem_u32(sa + kABytes));
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {      // 4 MMAs of 32 bytes of K each, either operand type
+            if (TF32) umma_tf32(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -1043,8 +1063,8 @@ inline bool tma_ok(const void* p, int64_t ld, int esize) {
   return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * esize) % 16 == 0;
 }
 
-inline int fill_ab(TcMaps& mp, TcArgs& ta, const GemmArgs& g, int64_t a_cols, int BN) {
-  VC_CHECK(g.K % BK == 0, "bf16 tensor-core GEMM needs K %% 64 == 0 (K=%d)", g.K);
+inline int fill_ab(TcMaps& mp, TcArgs& ta, const GemmArgs& g, int64_t a_cols, int BN, int esize = 2) {
+  VC_CHECK(g.K % (128 / esize) == 0, "tensor-core GEMM needs K to be a multiple of %d (K=%d)", 128 / esize, g.K);
   VC_CHECK(g.N % 4 == 0, "bf16 tensor-core GEMM needs N %% 4 == 0 (N=%d)", g.N);
   VC_CHECK(g.a_col0 % 8 == 0 && g.a_split % BK == 0 && g.a_skip % 8 == 0, "A column offsets must be multiples of 8/64");
   memset(&ta, 0, sizeof(ta));
@@ -1053,9 +1073,9 @@ inline int fill_ab(TcMaps& mp, TcArgs& ta, const GemmArgs& g, int64_t a_cols, in
     const int zz = z < g.nz ? z : 0;
     int c0 = 0;
     Ref ra{g.A[zz], g.a_origin, g.a_origin ? g.a_origin_cols : a_cols, g.lda};
-    VC_TRY(ref_map(&mp.A[z], &c0, ra, (uint64_t)g.M, BM, 2));
+    VC_TRY(ref_map(&mp.A[z], &c0, ra, (uint64_t)g.M, BM, esize));
     ta.a_col0[z] = c0 + g.a_col0;
-    VC_TRY(get_map(&mp.W[z], g.W[zz], (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, (uint32_t)BN, 2));
+    VC_TRY(get_map(&mp.W[z], g.W[zz], (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, (uint32_t)BN, esize));
   }
   return VC_OK;
 }
@@ -1129,6 +1149,30 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
     dim3 grid((g.N + 127) / 128, (g.M + BM - 1) / BM, 1);
     kern<<<grid, kThreads, smem, stream>>>(mp, ta);
   }
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ---- fp32 operands read as tf32 (feature projection): C[M,N] bf16 = A[M,K] fp32 . W[N,K]^T fp32 + bias
+inline int launch_gemm_tc_tf32(const GemmArgs& g, int64_t a_cols, const EpiStore<bf16, false, false>& e, cudaStream_t stream) {
+  if (g.M == 0 || g.N == 0) return VC_OK;
+  VC_CHECK(e.C2[0] == nullptr && g.nz == 1 && tma_ok(e.C[0], e.ldc, 2) && tma_ok(g.A[0], g.lda, 4) && tma_ok(g.W[0], g.ldw, 4) &&
+               g.N >= 256 && g.a_split >= g.K,
+           "tf32 GEMM: unsupported operand layout");
+  TcMaps mp;
+  TcArgs ta;
+  VC_TRY(fill_ab(mp, ta, g, a_cols, 256, 4));
+  ta.bias[0] = ta.bias[1] = e.bias[0];
+  VC_TRY(get_map(&mp.io[0], e.C[0], (uint64_t)g.M, (uint64_t)g.N, (uint64_t)e.ldc, BM, 2));
+  constexpr int kStages = 3;
+  const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 4 * kBoxBytes + 1024;
+  const int tm = (g.M + BM - 1) / BM, tn = (g.N + 255) / 256;
+  const int ctas = tm * tn < num_sms() ? tm * tn : num_sms();
+  VocabStats vs;
+  memset(&vs, 0, sizeof(vs));
+  auto kern = gemm_tc_persistent_kernel<kStages, EPI_STORE, bf16, false, false, true>;
+  VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<ctas, PersistentCfg<EPI_STORE>::kThreads, smem, stream>>>(mp, ta, tm, tn, vs);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
