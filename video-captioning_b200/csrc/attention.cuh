@@ -409,6 +409,12 @@ __device__ __forceinline__ __half2 additive4_h2(const uint4& key, const uint4& q
   return acc;
 }
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// coherent 16-byte load: for data written by the previous kernel of the stream and read after pdl_wait()
+__device__ __forceinline__ uint4 ld128(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
 
 // K: exact beam count; DH: warps sharing one frame (2: D in (256, 512], 1: D <= 256)
 template <int K, int DH>
@@ -641,10 +647,13 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) attn_additive_mma_kernel(co
   };
   stage_enc(0, 0);                               // lands during the scoring phase
 
-  // queries + score vector -> shared memory (fp16)
-  for (int i = tid; i < K * D / 8; i += kMmaThreads)
-    reinterpret_cast<uint4*>(q_s)[i] = ldg128(a.q + (int64_t)b * K * D + (int64_t)i * 8);
+  // score vector + queries -> shared memory (fp16).  enc_out, keys and v do not change during the decode loop:
+  // only the queries (and the ctx output) depend on the previous kernel in the stream (PDL, common.cuh).
   for (int i = tid; i < D / 8; i += kMmaThreads) reinterpret_cast<uint4*>(v_s)[i] = ldg128(a.v + (int64_t)i * 8);
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int i = tid; i < K * D / 8; i += kMmaThreads)
+    reinterpret_cast<uint4*>(q_s)[i] = ld128(a.q + (int64_t)b * K * D + (int64_t)i * 8);
   __syncthreads();
 
   // ---- scores: warp w owns feature blocks fb = w, w+4, ... (32 features each)
@@ -802,11 +811,11 @@ inline int launch_attn_additive_mma(const AttnAddArgs& a, int K, cudaStream_t st
     if (nbuf == 2) {                                                                                       \
       auto kern = attn_additive_mma_kernel<KK, 2, 4>;                                                      \
       VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-      kern<<<a.B, kMmaThreads, smem, stream>>>(a);                                                         \
+      VC_CUDA(launch_pdl(kern, dim3(a.B), dim3(kMmaThreads), smem, stream, a));                            \
     } else {                                                                                               \
       auto kern = attn_additive_mma_kernel<KK, 1, 7>;                                                      \
       VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-      kern<<<a.B, kMmaThreads, smem, stream>>>(a);                                                         \
+      VC_CUDA(launch_pdl(kern, dim3(a.B), dim3(kMmaThreads), smem, stream, a));                            \
     }                                                                                                      \
   } while (0)
   switch (K) {

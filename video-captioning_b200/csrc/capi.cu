@@ -786,8 +786,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
     VC_CUDA(cudaGetLastError());
     if (step + 1 < S) {
       VC_SCOPE(VC_CLS_REORDER_EMBED);
-      reorder_embed_kernel<ActT><<<R, 128, 0, s>>>(st, parent, w.cur_tok, V);
-      VC_CUDA(cudaGetLastError());
+      VC_CUDA(launch_pdl(reorder_embed_kernel<ActT>, dim3(R), dim3(128), 0, s, st, parent, (const int*)w.cur_tok, V));
     }
   }
   if (mode == DM_BEAM) {

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "vc_b200.h"
 
@@ -124,5 +126,40 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The decode loop is ~9 dependent launches per step, each 10-90 us: launch latency and kernel prologues (barrier init,
+// TMEM allocation, tensor-map fetch, loads of step-invariant data) are a visible share of the step.  Kernels launched
+// through launch_pdl may start while their predecessor in the stream is still running; they call pdl_wait() before
+// touching anything the predecessor writes (or reads: every global store comes after the wait), and
+// pdl_launch_dependents() right after it, so that at most one successor is resident ahead of time.
+// A kernel launched without the attribute returns from pdl_wait() immediately.  VC_DISABLE_PDL=1: plain launches (A/B).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VC_DISABLE_PDL");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 }  // namespace vc

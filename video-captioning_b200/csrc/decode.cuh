@@ -471,8 +471,8 @@ __global__ void __launch_bounds__(kSelWarps * 32) beam_select_kernel(
 // KMAX: compile-time bound of the beam size (loops are unrolled to it); MAXCL: chunk maxima per lane held in
 // registers (nc <= 32 * MAXCL).
 template <int KMAX, int MAXCL>
-__global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, const float* __restrict__ logits, int64_t ld,
-                                                                 const float* __restrict__ cmax, const float2* __restrict__ part,
+__global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, const float* logits, int64_t ld,
+                                                                 const float* cmax, const float2* part,
                                                                  int nc, int np, int B, int K, int V, int S, int step, int end_id,
                                                                  float length_penalty, int* __restrict__ parent,
                                                                  int* __restrict__ cur_tok, int greedy, int* __restrict__ tokens_out) {
@@ -483,13 +483,15 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
   const int b = blockIdx.x;
   const int64_t r = (int64_t)b * K + k;
   constexpr float kL2e = 1.4426950408889634f;
+  pdl_wait();                 // logits / cmax / part come from the vocabulary GEMM just before (read with ld.cg: PDL, common.cuh)
+  pdl_launch_dependents();
 
   // chunk maxima first (the longest dependent chain starts here)
   float cv[MAXCL];
 #pragma unroll
   for (int i = 0; i < MAXCL; ++i) {
     const int c = lane + 32 * i;
-    cv[i] = (c < nc) ? __ldg(cmax + r * nc + c) : -INFINITY;
+    cv[i] = (c < nc) ? __ldcg(cmax + r * nc + c) : -INFINITY;
   }
   // 1. log-sum-exp of the row
   float lse;
@@ -499,16 +501,16 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int j = lane + 32 * i;
-      p[i] = (j < np) ? __ldg(part + r * np + j) : make_float2(-1e30f, 0.f);
+      p[i] = (j < np) ? __ldcg(part + r * np + j) : make_float2(-1e30f, 0.f);
       m = fmaxf(m, p[i].x);
     }
-    for (int j = lane + 96; j < np; j += 32) m = fmaxf(m, __ldg(part + r * np + j).x);
+    for (int j = lane + 96; j < np; j += 32) m = fmaxf(m, __ldcg(part + r * np + j).x);
     m = warp_max(m);
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; ++i) sum += p[i].y * exp2f((p[i].x - m) * kL2e);
     for (int j = lane + 96; j < np; j += 32) {
-      const float2 pp = __ldg(part + r * np + j);
+      const float2 pp = __ldcg(part + r * np + j);
       sum += pp.y * exp2f((pp.x - m) * kL2e);
     }
     sum = warp_sum(sum);
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
       if (wi != 0x7fffffff) {
         const int col = wi * 32 + lane;
         cidx[sel] = col;
-        if (col < V) val[sel] = __ldg(logits + r * ld + col);
+        if (col < V) val[sel] = __ldcg(logits + r * ld + col);
       }
     }
   }
@@ -587,7 +589,7 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
 inline int launch_select_fused(BeamState bs, const float* logits, int64_t ld, const float* cmax, const float2* part, int nc, int np,
                                int B, int K, int V, int S, int step, int end_id, float lp, int* parent, int* cur_tok, int greedy,
                                int* tokens_out, cudaStream_t s) {
-#define VC_SEL(KM, CL) select_fused_kernel<KM, CL><<<B, K * 32, 0, s>>>(bs, logits, ld, cmax, part, nc, np, B, K, V, S, step, end_id, lp, parent, cur_tok, greedy, tokens_out)
+#define VC_SEL(KM, CL) VC_CUDA(launch_pdl(select_fused_kernel<KM, CL>, dim3(B), dim3(K * 32), 0, s, bs, logits, ld, cmax, part, nc, np, B, K, V, S, step, end_id, lp, parent, cur_tok, greedy, tokens_out))
 #define VC_SEL_K(CL)                     \
   do {                                   \
     if (K == 1) VC_SEL(1, CL);           \
@@ -609,10 +611,11 @@ inline int launch_select_fused(BeamState bs, const float* logits, int64_t ld, co
 // video_captioning_model.py:247-249,269-272 (clone/cat of the kept (h,c) columns) and decoder.py:130 for
 // the next step.  One CTA per row: gathers the parent row's new state into this row's GEMM operands.
 template <class ActT>
-__global__ void __launch_bounds__(128) reorder_embed_kernel(DecState<ActT> st, const int* __restrict__ parent,
-                                                            const int* __restrict__ cur_tok, int V) {
+__global__ void __launch_bounds__(128) reorder_embed_kernel(DecState<ActT> st, const int* parent, const int* cur_tok, int V) {
   const int r = blockIdx.x;
-  const int p = parent ? parent[r] : r;
+  pdl_wait();                 // parent / cur_tok come from the selection kernel just before (PDL, common.cuh)
+  pdl_launch_dependents();
+  const int p = parent ? __ldcg(parent + r) : r;
   for (int l = 0; l < st.L; ++l) {
     const ActT* hs = st.h_new[l] + (int64_t)p * st.H;
     const float* cs = st.c_new[l] + (int64_t)p * st.H;
@@ -625,7 +628,7 @@ __global__ void __launch_bounds__(128) reorder_embed_kernel(DecState<ActT> st, c
       *reinterpret_cast<float4*>(cd + u) = *reinterpret_cast<const float4*>(cs + u);
     }
   }
-  int tok = cur_tok[r];
+  int tok = __ldcg(cur_tok + r);
   tok = min(max(tok, 0), V - 1);
   const ActT* e = st.emb_table + (int64_t)tok * st.E;
   ActT* ed = st.emb_dst + (int64_t)r * st.emb_ld;

@@ -223,6 +223,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs g) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();                 // everything above overlaps the tail of the previous kernel in the stream
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -529,6 +531,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();                 // everything above overlaps the tail of the previous kernel in the stream
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -895,6 +899,8 @@ gemm_tc_direct_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();                 // everything above overlaps the tail of the previous kernel in the stream
+  pdl_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -1090,7 +1096,7 @@ int launch_direct(const GemmArgs& g, int64_t a_cols, const Epi& epi, cudaStream_
   auto kern = gemm_tc_direct_kernel<128, kStages, 2, Epi>;
   VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.N + 127) / 128, (g.M + BM - 1) / BM, g.nz);
-  kern<<<grid, kThreads, smem, stream>>>(mp, ta, epi);
+  VC_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, mp, ta, epi));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -1132,14 +1138,14 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
         const size_t smem_st = (size_t)kStatStages * (BM * BK * 2 + 256 * BK * 2) + 256 * 144 + 1024;
         auto kern = gemm_tc_persistent_kernel<kStatStages, EPI_STORE, OutT, TANH, true>;
         VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st));
-        kern<<<ctas, PersistentCfg<EPI_STORE>::kThreads, smem_st, stream>>>(mp, ta, tm, tn, vs);
+        VC_CUDA(launch_pdl(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem_st, stream, mp, ta, tm, tn, vs));
         VC_CUDA(cudaGetLastError());
         return VC_OK;
       }
     }
     auto kern = gemm_tc_persistent_kernel<kStages, EPI_STORE, OutT, TANH, false>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<ctas, PersistentCfg<EPI_STORE>::kThreads, smem, stream>>>(mp, ta, tm, tn, vs);
+    VC_CUDA(launch_pdl(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem, stream, mp, ta, tm, tn, vs));
   } else {
     // 3 stages x 32 KB: two CTAs co-reside per SM, so one CTA's epilogue overlaps the other's main loop
     constexpr int kStages = 3;
@@ -1147,7 +1153,7 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
     auto kern = gemm_tc_kernel<128, kStages, 2, EPI_STORE, OutT, TANH, false>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((g.N + 127) / 128, (g.M + BM - 1) / BM, 1);
-    kern<<<grid, kThreads, smem, stream>>>(mp, ta);
+    VC_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, mp, ta));
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
@@ -1172,7 +1178,7 @@ inline int launch_gemm_tc_tf32(const GemmArgs& g, int64_t a_cols, const EpiStore
   memset(&vs, 0, sizeof(vs));
   auto kern = gemm_tc_persistent_kernel<kStages, EPI_STORE, bf16, false, false, true>;
   VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<ctas, PersistentCfg<EPI_STORE>::kThreads, smem, stream>>>(mp, ta, tm, tn, vs);
+  VC_CUDA(launch_pdl(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem, stream, mp, ta, tm, tn, vs));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -1214,7 +1220,7 @@ inline int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiLstm<bf16,
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VocabStats vs;
     memset(&vs, 0, sizeof(vs));
-    kern<<<num_sms(), PersistentCfg<EPI_LSTM>::kThreads, smem, stream>>>(mp, ta, (int)grid.y, (int)grid.x, vs);
+    VC_CUDA(launch_pdl(kern, dim3(num_sms()), dim3(PersistentCfg<EPI_LSTM>::kThreads), smem, stream, mp, ta, (int)grid.y, (int)grid.x, vs));
     VC_CUDA(cudaGetLastError());
     return VC_OK;
   }
@@ -1223,13 +1229,13 @@ inline int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiLstm<bf16,
     const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + (size_t)(4 + 2) * kBoxBytes + 1024;
     auto kern = gemm_tc_kernel<256, kStages, 1, EPI_LSTM, bf16, false, true>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, stream>>>(mp, ta);
+    VC_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, mp, ta));
   } else {
     constexpr int kStages = 3;
     const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + (size_t)2 * kBoxBytes + 1024;
     auto kern = gemm_tc_kernel<256, kStages, 1, EPI_LSTM, bf16, false, false>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, stream>>>(mp, ta);
+    VC_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, mp, ta));
   }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
