@@ -146,6 +146,57 @@ def test_masked_encoder_vs_oracle():
     assert torch.equal(out["generated_tokens"].cpu(), ref["generated_tokens"])
 
 
+@pytest.mark.parametrize("B,K,groups", [(3, 5, "41"), (5, 1, "31"), (7, 3, "42"), (300, 5, "41"), (310, 5, "51")])
+def test_persistent_attention_kernel(monkeypatch, B, K, groups):
+    """bf16 additive attention, persistent warp-specialised kernel (attention.cuh v5: unit-interleaved scoring groups,
+    online softmax in the context groups): context and weights against the oracle (2e-2) and against the one-CTA-per-
+    video kernel v4 (same arithmetic up to summation order), with a ragged mask; small batches (fewer CTAs than SMs,
+    one video per CTA) and a batch with several videos per CTA."""
+    from oracle import synth
+    cfg = synth.make_config("small")
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, "bahdanau", seed=43)
+    o = make_oracle(sd)
+    T, H = cfg.model.video_sequence_length, cfg.model.encoder_hidden_dim
+    rng = np.random.default_rng(B * 10 + K)
+    enc = torch.from_numpy(rng.standard_normal((B, T, H), dtype=np.float32))
+    hid = torch.from_numpy(rng.standard_normal((B * K, H), dtype=np.float32))
+    mask = torch.ones(B, T)
+    mask[1, T - 5:] = 0
+    mask[B - 1, : T // 2] = 0
+    ctx_o, w_o = o.attend(enc.repeat_interleave(K, 0), hid, mask.repeat_interleave(K, 0))
+    out = {}
+    for variant in ("5", "4"):
+        monkeypatch.setenv("VC_ATTN_VARIANT", variant)
+        monkeypatch.setenv("VC_ATTN_WS_MIN_B", "1")
+        monkeypatch.setenv("VC_ATTN_GROUPS", groups)
+        mb = make_native_model(cfg, V, sd, "bahdanau", "bf16")
+        ctx, w = mb._handle().attention_step(enc.cuda(), hid.cuda(), mask.cuda(), K)
+        out[variant] = (ctx.float().cpu().numpy(), w.cpu().numpy())
+        assert np.abs(out[variant][1] - w_o.numpy()).max() < 2e-2 and rel_err(out[variant][0], ctx_o) < 2e-2
+        assert np.abs(out[variant][1].sum(-1) - 1).max() < 1e-4
+    assert np.abs(out["5"][1] - out["4"][1]).max() < 1e-4          # weights: fp32 softmax in both
+    assert rel_err(out["5"][0], out["4"][0]) < 1e-2                # context: bf16 outputs, different summation order
+
+
+def test_persistent_attention_in_beam_decode(monkeypatch):
+    """Beam decode (no attention weights requested) through the persistent attention kernel vs the v4 kernel: bf16
+    free-running tokens may only differ where two logits nearly tie, so nearly all rows must be identical."""
+    from oracle import synth
+    cfg = synth.make_config("small")
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, "bahdanau", seed=7, logit_gain=8.0, end_token_id=END, end_bias=0.3)
+    x = torch.from_numpy(synth.make_features(300, cfg.model.video_sequence_length, cfg.model.cnn_feature_dim, seed=9)).cuda()
+    toks = {}
+    for variant in ("5", "4"):
+        monkeypatch.setenv("VC_ATTN_VARIANT", variant)
+        monkeypatch.setenv("VC_ATTN_WS_MIN_B", "1")
+        m = make_native_model(cfg, V, sd, "bahdanau", "bf16")
+        toks[variant] = m.generate(x, START, END, max_length=12, method="beam", beam_size=5)["generated_tokens"].cpu()
+    same = (toks["5"] == toks["4"]).all(dim=1).float().mean().item()
+    assert same >= 0.97, same
+
+
 # ------------------------------------------------------------------ size-independent properties at full size
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_full_size_properties_msvd(precision):

@@ -789,6 +789,417 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) attn_additive_mma_kernel(co
   }
 }
 
+// ---------------------------------------------------------------- additive attention, bf16 mode (v5: one persistent, warp-specialised CTA per SM)
+// v4 above runs the MUFU-bound scoring of all resident CTAs first and their memory/tensor-bound context phases
+// afterwards (every CTA of the single wave starts together), so the XU pipe idles ~40% of the kernel.  v5 decouples the
+// two and streams over (video, 16-frame tile) units with an online softmax.  One CTA per SM owns the videos
+// b = blockIdx.x + i*gridDim.x; its units are numbered u = i*NT + tile:
+//   NG scoring groups of 4 warps   group j takes the units u = j (mod NG): tanh tile x v on mma.sync exactly as in v4
+//                                  (warp = 4 of the D/32 feature blocks), partial dot products -> a ring of shared-memory
+//                                  slots (mbarrier full/empty).  Interleaving by unit, not by video, balances the groups
+//                                  to within one tile (7 videos x 5 tiles over 4 groups: 9/9/9/8); every warp keeps a
+//                                  private double-buffered copy of the query columns it needs, so scoring warps never
+//                                  meet at a block barrier.
+//   NCG context groups of 4 warps  group c takes the videos i = c (mod NCG): sums the four partials of a unit, running
+//                                  max / sum (flash-attention style rescaling of the fp32 accumulators), weights split
+//                                  into bf16 hi+lo, enc^T x weights on mma.sync from a ring of enc tiles.
+//   1 producer warp                fills the enc ring with cp.async.bulk (mbarrier tx), as far ahead as the ring allows.
+// When the attention weights are requested the raw scores of a video stay in shared memory and are normalised with
+// the final (max, sum) at the end of the video.
+constexpr int kWsPartSlots = 8;
+constexpr int kWsEncSlots = 6;
+
+__device__ __forceinline__ void amb_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void amb_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void amb_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool amb_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void amb_wait(uint32_t bar, uint32_t parity) {   // bounded: a protocol bug traps instead of hanging
+  for (uint32_t n = 0; !amb_try(bar, parity); ++n)
+    if (n > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// ring bookkeeping: advance (slot, parity) by n positions in a ring of N slots
+__device__ __forceinline__ void ring_adv(int& slot, uint32_t& par, int n, int N) {
+  slot += n;
+  while (slot >= N) { slot -= N; par ^= 1u; }
+}
+
+// T_weights: number of frames when the attention weights are requested (raw scores are kept per video), else 0
+inline size_t attn_ws_smem_bytes(int K, int D, int H, int NG, int NCG, int T_weights) {
+  const int Tp = (T_weights + 15) & ~15;
+  return (size_t)D * 2 + (size_t)NG * 4 * 2 * K * 128 * 2 + (size_t)kWsPartSlots * 4 * K * 16 * 4 + (size_t)NCG * K * H * 2 +
+         (size_t)kWsEncSlots * 16 * (H + kEncPad) * 2 + (size_t)(2 * kWsPartSlots + 2 * kWsEncSlots) * 8 +
+         (T_weights > 0 ? (size_t)NCG * (K * Tp * 4 + K * 8) : 0);
+}
+
+// K: exact beam count (<= 8).  Requires D % 32 == 0, D <= 512, H % 64 == 0, H <= 512.
+template <int K, int NG, int NCG>
+__global__ void __launch_bounds__(32 * (4 * NG + 4 * NCG + 1), 1) attn_additive_ws_kernel(const AttnAddArgs a) {
+  constexpr int kScoreWarps = 4 * NG, kCtxWarps = 4 * NCG;
+  constexpr int kThreads = 32 * (kScoreWarps + kCtxWarps + 1);
+  extern __shared__ __align__(16) uint8_t smem_u8[];
+  const int T = a.T, D = a.D, H = a.H, B = a.B;
+  const int NT = (T + 15) >> 4;                  // 16-frame tiles
+  const int pitch = H + kEncPad;                 // staged enc row pitch (elements)
+  __half* v_s = reinterpret_cast<__half*>(smem_u8);                              // [D]
+  __half* q_s = v_s + D;                                                         // [scoring warp][2][K][4 blocks][32]
+  float* part = reinterpret_cast<float*>(q_s + (size_t)kScoreWarps * 2 * K * 128); // [slots][4 warps][K][16]
+  bf16* out_s = reinterpret_cast<bf16*>(part + kWsPartSlots * 4 * K * 16);       // [NCG][K][H]
+  bf16* enc_s = out_s + (size_t)NCG * K * H;                                     // [slots][16][pitch]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(enc_s + (size_t)kWsEncSlots * 16 * pitch);
+  const uint32_t part_full = (uint32_t)__cvta_generic_to_shared(bars);
+  const uint32_t part_empty = part_full + 8u * kWsPartSlots;
+  const uint32_t enc_full = part_empty + 8u * kWsPartSlots;
+  const uint32_t enc_empty = enc_full + 8u * kWsEncSlots;
+  float2* ml_all = reinterpret_cast<float2*>(bars + 2 * kWsPartSlots + 2 * kWsEncSlots);   // [NCG][K] (max, 1/sum)      } only when the
+  float* sc_all = reinterpret_cast<float*>(ml_all + NCG * K);                              // [NCG][K][NT*16] raw scores } weights are requested
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int nvid = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // videos of this CTA
+  const int total = nvid * NT;                                                    // units of this CTA
+
+  if (tid == 0) {
+    for (int i = 0; i < kWsPartSlots; ++i) { amb_init(part_full + 8u * i, 4); amb_init(part_empty + 8u * i, 4); }
+    for (int i = 0; i < kWsEncSlots; ++i) { amb_init(enc_full + 8u * i, 1); amb_init(enc_empty + 8u * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < D / 8; i += kThreads) reinterpret_cast<uint4*>(v_s)[i] = ldg128(a.v + (int64_t)i * 8);
+  __syncthreads();
+
+  // enc tile `ft` of video index `vi` -> ring slot
+  auto issue_enc = [&](int vi, int ft, int slot) {
+    const uint32_t fb = enc_full + 8u * slot;
+    amb_expect_tx(fb, 16u * (uint32_t)H * 2u);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(enc_s + (size_t)slot * 16 * pitch);
+    const bf16* src = a.values + (int64_t)((int)blockIdx.x + vi * (int)gridDim.x) * T * H;
+    for (int rr = 0; rr < 16; ++rr) {
+      int t = ft * 16 + rr;
+      t = t < T ? t : T - 1;                     // frames past T: any finite row (their weights are zero)
+      bulk_g2s(dst + (uint32_t)(rr * pitch) * 2u, src + (int64_t)t * H, (uint32_t)H * 2u, fb);
+    }
+  };
+  // producer state (lane 0 of the last warp): the first ring pass does not depend on the previous kernel (PDL, common.cuh)
+  int p_u = 0, p_vi = 0, p_ft = 0;
+  if (warp == kScoreWarps + kCtxWarps && lane == 0) {
+    for (; p_u < total && p_u < kWsEncSlots; ++p_u) {
+      issue_enc(p_vi, p_ft, p_u);
+      if (++p_ft == NT) { p_ft = 0; ++p_vi; }
+    }
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp < kScoreWarps) {
+    // ================= scoring warps
+    const int gi = warp >> 2, sw = warp & 3;
+    const int nfb = D / 32;
+    __half* q_w = q_s + (size_t)warp * 2 * K * 128;
+    // this warp's query columns (feature blocks sw, sw+4, ...) of video b -> private buffer
+    auto load_q = [&](int b, int buf) {
+      const __half* src = a.q + (int64_t)b * K * D;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(q_w + (size_t)buf * K * 128);
+      for (int i = lane; i < K * 16; i += 32) {  // i = (k*4 + j)*4 + c: 16-byte chunk c of block j of beam k
+        const int c = i & 3, j = (i >> 2) & 3, k = i >> 4;
+        const int fb = sw + 4 * j;
+        if (fb < nfb) cp_async16(dst + (uint32_t)i * 16u, src + (int64_t)k * D + fb * 32 + c * 8);
+      }
+      cp_async_commit();
+    };
+    int u = gi, vi = gi / NT, ft = gi - (gi / NT) * NT;
+    int pslot = gi;
+    uint32_t ppar = 0;
+    ring_adv(pslot, ppar, 0, kWsPartSlots);
+    int qb = 1, q_vi = -1;
+    uint4 key0 = make_uint4(0u, 0u, 0u, 0u), key1 = key0;
+    if (u < total) {
+      const int b = (int)blockIdx.x + vi * (int)gridDim.x;
+      load_q(b, 0);
+      if (sw < nfb) {
+        int t0 = ft * 16 + g, t1 = t0 + 8;
+        t0 = t0 < T ? t0 : T - 1;
+        t1 = t1 < T ? t1 : T - 1;
+        const __half* kb = a.keys + (int64_t)b * T * D + tg * 8 + sw * 32;
+        key0 = ldg128(kb + (int64_t)t0 * D);
+        key1 = ldg128(kb + (int64_t)t1 * D);
+      }
+    }
+    while (u < total) {
+      const int b = (int)blockIdx.x + vi * (int)gridDim.x;
+      // next unit of this group
+      int vin = vi, ftn = ft + NG;
+      while (ftn >= NT) { ftn -= NT; ++vin; }
+      const bool has_next = u + NG < total;
+      if (vi != q_vi) {                          // queries of this video were prefetched into the other buffer
+        cp_async_wait<0>();
+        __syncwarp();
+        qb ^= 1;
+        q_vi = vi;
+      }
+      if (has_next && vin != vi) load_q((int)blockIdx.x + vin * (int)gridDim.x, qb ^ 1);
+      const __half* q = q_w + (size_t)qb * K * 128 + tg * 8;
+      int t0 = ft * 16 + g, t1 = t0 + 8;
+      t0 = t0 < T ? t0 : T - 1;
+      t1 = t1 < T ? t1 : T - 1;
+      const __half* kbase = a.keys + (int64_t)b * T * D + tg * 8;
+      const __half* k0p = kbase + (int64_t)t0 * D;
+      const __half* k1p = kbase + (int64_t)t1 * D;
+      int n0 = ftn * 16 + g, n1 = n0 + 8;        // same lanes, first block of the next unit
+      n0 = n0 < T ? n0 : T - 1;
+      n1 = n1 < T ? n1 : T - 1;
+      const __half* nbase = a.keys + (int64_t)((int)blockIdx.x + vin * (int)gridDim.x) * T * D + tg * 8 + sw * 32;
+      float acc[K][4];
+#pragma unroll
+      for (int k = 0; k < K; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
+      for (int fb = sw, j = 0; fb < nfb; fb += 4, ++j) {
+        uint4 nx0 = make_uint4(0u, 0u, 0u, 0u), nx1 = nx0;
+        if (fb + 4 < nfb) {
+          nx0 = ldg128(k0p + (fb + 4) * 32);
+          nx1 = ldg128(k1p + (fb + 4) * 32);
+        } else if (has_next) {
+          nx0 = ldg128(nbase + (int64_t)n0 * D);
+          nx1 = ldg128(nbase + (int64_t)n1 * D);
+        }
+        const uint4 v4 = *reinterpret_cast<const uint4*>(v_s + fb * 32 + tg * 8);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const uint4 q4 = *reinterpret_cast<const uint4*>(q + k * 128 + j * 32);
+          mma_f16(acc[k], tanh_h2(key0.x, q4.x), tanh_h2(key1.x, q4.x), tanh_h2(key0.y, q4.y), tanh_h2(key1.y, q4.y), v4.x, v4.y);
+          mma_f16(acc[k], tanh_h2(key0.z, q4.z), tanh_h2(key1.z, q4.z), tanh_h2(key0.w, q4.w), tanh_h2(key1.w, q4.w), v4.z, v4.w);
+        }
+        key0 = nx0;
+        key1 = nx1;
+      }
+      amb_wait(part_empty + 8u * pslot, ppar ^ 1u);
+      if (tg == 0) {
+        float* pp = part + (size_t)(pslot * 4 + sw) * K * 16;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          pp[k * 16 + g] = acc[k][0];            // every column of the accumulator tile holds the dot product
+          pp[k * 16 + g + 8] = acc[k][2];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) amb_arrive(part_full + 8u * pslot);
+      ring_adv(pslot, ppar, NG, kWsPartSlots);
+      u += NG;
+      vi = vin;
+      ft = ftn;
+    }
+  } else if (warp < kScoreWarps + kCtxWarps) {
+    // ================= context warps
+    const int cg = (warp - kScoreWarps) >> 2, cw = (warp - kScoreWarps) & 3, ctid = tid - 32 * kScoreWarps - 128 * cg;
+    const int cwid = H / 4;                      // columns per warp
+    const int nmt = cwid / 16;                   // m-tiles per warp (8 at H = 512)
+    constexpr int MAXMT = 8;
+    constexpr float kL2e = 1.4426950408889634f;
+    bf16* outg = out_s + (size_t)cg * K * H;
+    float2* ml_s = ml_all + cg * K;
+    float* sc_s = sc_all + (size_t)cg * K * NT * 16;
+    int pslot = 0, eslot = 0;
+    uint32_t ppar = 0, epar = 0;
+    ring_adv(pslot, ppar, cg * NT, kWsPartSlots);
+    ring_adv(eslot, epar, cg * NT, kWsEncSlots);
+    const int lrow = ((lane >> 4) << 3) + (lane & 7), lcol = ((lane >> 3) & 1) << 3;   // ldmatrix row address of this lane
+    for (int vi = cg; vi < nvid; vi += NCG) {
+      const int b = (int)blockIdx.x + vi * (int)gridDim.x;
+      float c[MAXMT][4];
+#pragma unroll
+      for (int i = 0; i < MAXMT; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
+      float m_run = -1e30f, l_run = 0.f;
+      for (int ft = 0; ft < NT; ++ft) {
+        // scores of beam g for frames ft*16 + {2tg, 2tg+1, 2tg+8, 2tg+9}
+        amb_wait(part_full + 8u * pslot, ppar);
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+        if (g < K) {
+          const float* pp = part + (size_t)pslot * 4 * K * 16 + g * 16 + 2 * tg;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float2 lo = *reinterpret_cast<const float2*>(pp + w * K * 16);
+            const float2 hi = *reinterpret_cast<const float2*>(pp + w * K * 16 + 8);
+            x0 += lo.x; x1 += lo.y; x2 += hi.x; x3 += hi.y;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) amb_arrive(part_empty + 8u * pslot);
+        ring_adv(pslot, ppar, 1, kWsPartSlots);
+        // bias, mask (attention.py:61), frames past T
+        const int tb = ft * 16 + 2 * tg;
+        float xs[4] = {x0 + a.v_bias, x1 + a.v_bias, x2 + a.v_bias, x3 + a.v_bias};
+        const int ts[4] = {tb, tb + 1, tb + 8, tb + 9};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (ts[i] >= T) xs[i] = -INFINITY;
+          else if (a.mask != nullptr && a.mask[(int64_t)b * T + ts[i]] == 0.f) xs[i] = -1e9f;
+        }
+        if (a.attn_out != nullptr && cw == 0 && g < K) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sc_s[g * NT * 16 + ts[i]] = xs[i];
+        }
+        // online softmax over the tile (the 4 lanes of a group hold the 16 frames of beam g)
+        float tmax = fmaxf(fmaxf(xs[0], xs[1]), fmaxf(xs[2], xs[3]));
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 2));
+        const float m_new = fmaxf(m_run, tmax);
+        float scale = exp2f((m_run - m_new) * kL2e);
+        float pv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pv[i] = exp2f((xs[i] - m_new) * kL2e);
+        float psum = (pv[0] + pv[1]) + (pv[2] + pv[3]);
+        psum += __shfl_xor_sync(0xffffffffu, psum, 1);
+        psum += __shfl_xor_sync(0xffffffffu, psum, 2);
+        l_run = l_run * scale + psum;
+        m_run = m_new;
+        if (g >= K) { scale = 1.f; pv[0] = pv[1] = pv[2] = pv[3] = 0.f; }
+        // accumulator columns of this lane are beams 2tg, 2tg+1: their rescale factors live in lanes 8tg, 8tg+4
+        const float sc0 = __shfl_sync(0xffffffffu, scale, 8 * tg);
+        const float sc1 = __shfl_sync(0xffffffffu, scale, 8 * tg + 4);
+        if (ft > 0) {
+#pragma unroll
+          for (int i = 0; i < MAXMT; ++i) { c[i][0] *= sc0; c[i][1] *= sc1; c[i][2] *= sc0; c[i][3] *= sc1; }
+        }
+        uint32_t bh0, bl0, bh1, bl1;
+        split_bf16x2(pv[0], pv[1], bh0, bl0);
+        split_bf16x2(pv[2], pv[3], bh1, bl1);
+        // context: ctx^T[col, beam] += enc[t, col] * p[beam, t]
+        amb_wait(enc_full + 8u * eslot, epar);
+        const uint32_t tile = (uint32_t)__cvta_generic_to_shared(enc_s + (size_t)eslot * 16 * pitch);
+#pragma unroll
+        for (int i = 0; i < MAXMT; ++i) {
+          if (i < nmt) {
+            const int col0 = cw * cwid + i * 16;
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4_trans(tile + (uint32_t)(lrow * pitch + col0 + lcol) * 2u, a0, a1, a2, a3);
+            mma_bf16(c[i], a0, a1, a2, a3, bh0, bh1);
+            mma_bf16(c[i], a0, a1, a2, a3, bl0, bl1);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) amb_arrive(enc_empty + 8u * eslot);
+        ring_adv(eslot, epar, 1, kWsEncSlots);
+      }
+      ring_adv(pslot, ppar, (NCG - 1) * NT, kWsPartSlots);      // the units of the other groups' videos
+      ring_adv(eslot, epar, (NCG - 1) * NT, kWsEncSlots);
+      // normalise and store: c[i] = {ctx[col0+g][2tg], ctx[col0+g][2tg+1], ctx[col0+g+8][2tg], ctx[col0+g+8][2tg+1]} (col, beam)
+      const float inv = (g < K) ? 1.0f / l_run : 0.f;
+      const float i0 = __shfl_sync(0xffffffffu, inv, 8 * tg);
+      const float i1 = __shfl_sync(0xffffffffu, inv, 8 * tg + 4);
+      named_bar_sync(1 + cg, 128);               // the previous video's rows have left the staging buffer
+      if (a.attn_out != nullptr && cw == 0 && g < K && tg == 0) ml_s[g] = make_float2(m_run, inv);
+      const int k0 = 2 * tg, k1 = 2 * tg + 1;
+#pragma unroll
+      for (int i = 0; i < MAXMT; ++i) {
+        if (i < nmt) {
+          const int col0 = cw * cwid + i * 16;
+          if (k0 < K) { outg[k0 * H + col0 + g] = __float2bfloat16_rn(c[i][0] * i0); outg[k0 * H + col0 + g + 8] = __float2bfloat16_rn(c[i][2] * i0); }
+          if (k1 < K) { outg[k1 * H + col0 + g] = __float2bfloat16_rn(c[i][1] * i1); outg[k1 * H + col0 + g + 8] = __float2bfloat16_rn(c[i][3] * i1); }
+        }
+      }
+      named_bar_sync(1 + cg, 128);
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        for (int c8 = ctid * 8; c8 < H; c8 += 128 * 8)
+          *reinterpret_cast<uint4*>(a.ctx + ((int64_t)b * K + k) * a.ctx_ld + c8) = *reinterpret_cast<const uint4*>(outg + k * H + c8);
+      if (a.attn_out != nullptr) {               // attention weights (attention.py:64) from the raw scores and the final (max, sum)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float2 ml = ml_s[k];
+          for (int t = ctid; t < T; t += 128)
+            a.attn_out[((int64_t)b * K + k) * a.attn_ld + t] = exp2f((sc_s[k * NT * 16 + t] - ml.x) * kL2e) * ml.y;
+        }
+        named_bar_sync(1 + cg, 128);             // before the next video's scores overwrite sc_s
+      }
+    }
+  } else if (lane == 0) {
+    // ================= enc tile producer: as far ahead as the ring allows
+    int slot = 0;
+    uint32_t par = 0;
+    ring_adv(slot, par, p_u, kWsEncSlots);
+    for (; p_u < total; ++p_u) {
+      amb_wait(enc_empty + 8u * slot, par ^ 1u);
+      issue_enc(p_vi, p_ft, slot);
+      if (++p_ft == NT) { p_ft = 0; ++p_vi; }
+      ring_adv(slot, par, 1, kWsEncSlots);
+    }
+  }
+}
+
+inline int attn_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+inline int attn_ws_groups() {          // VC_ATTN_GROUPS=NG*10+NCG: scoring / context groups per CTA (A/B testing); default 41
+  const char* e = getenv("VC_ATTN_GROUPS");
+  const int v = e != nullptr ? atoi(e) : 41;
+  return (v == 31 || v == 41 || v == 42 || v == 51 || v == 52) ? v : 41;
+}
+// The persistent kernel needs at least two videos per SM to beat v4 (one CTA per video); VC_ATTN_WS_MIN_B overrides the
+// threshold (tests run it on small batches)
+inline bool attn_additive_ws_ok(int B, int K, int D, int H, int T, bool weights) {
+  const int cfg = attn_ws_groups();
+  const char* e = getenv("VC_ATTN_WS_MIN_B");
+  const int min_b = e != nullptr ? atoi(e) : 2 * attn_num_sms();
+  return B >= min_b && K >= 1 && K <= 8 && D % 32 == 0 && D <= 512 && H % 64 == 0 && H <= 512 && T >= 1 &&
+         attn_ws_smem_bytes(K, D, H, cfg / 10, cfg % 10, weights ? T : 0) <= 200 * 1024;
+}
+template <int NG, int NCG>
+int launch_attn_additive_ws_cfg(const AttnAddArgs& a, int K, cudaStream_t stream) {
+  const size_t smem = attn_ws_smem_bytes(K, a.D, a.H, NG, NCG, a.attn_out != nullptr ? a.T : 0);
+  const int grid = a.B < attn_num_sms() ? a.B : attn_num_sms();
+  constexpr int kThreads = 32 * (4 * NG + 4 * NCG + 1);
+#define VC_WS_LAUNCH(KK)                                                                               \
+  do {                                                                                                 \
+    auto kern = attn_additive_ws_kernel<KK, NG, NCG>;                                                  \
+    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    VC_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, a));                            \
+  } while (0)
+  switch (K) {
+    case 1: VC_WS_LAUNCH(1); break;
+    case 2: VC_WS_LAUNCH(2); break;
+    case 3: VC_WS_LAUNCH(3); break;
+    case 4: VC_WS_LAUNCH(4); break;
+    case 5: VC_WS_LAUNCH(5); break;
+    case 6: VC_WS_LAUNCH(6); break;
+    case 7: VC_WS_LAUNCH(7); break;
+    default: VC_WS_LAUNCH(8); break;
+  }
+#undef VC_WS_LAUNCH
+  return VC_OK;
+}
+inline int launch_attn_additive_ws(const AttnAddArgs& a, int K, cudaStream_t stream) {
+  VC_CHECK(attn_additive_ws_ok(a.B, K, a.D, a.H, a.T, a.attn_out != nullptr), "additive attention (ws): B=%d K=%d D=%d H=%d T=%d not supported",
+           a.B, K, a.D, a.H, a.T);
+  VC_CHECK(a.ctx_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ctx) & 15) == 0, "additive attention (ws): ctx must be 16-byte aligned");
+  switch (attn_ws_groups()) {
+    case 31: return launch_attn_additive_ws_cfg<3, 1>(a, K, stream);
+    case 42: return launch_attn_additive_ws_cfg<4, 2>(a, K, stream);
+    case 51: return launch_attn_additive_ws_cfg<5, 1>(a, K, stream);
+    case 52: return launch_attn_additive_ws_cfg<5, 2>(a, K, stream);
+    default: return launch_attn_additive_ws_cfg<4, 1>(a, K, stream);
+  }
+}
+
 inline int attn_mma_nbuf() {           // VC_ATTN_NBUF=2: double-buffered enc staging, 4 CTAs/SM; 1 (default): single buffer, 7 CTAs/SM
   static int n = 0;
   if (n == 0) { const char* e = getenv("VC_ATTN_NBUF"); n = (e != nullptr && e[0] == '2') ? 2 : 1; }

@@ -129,7 +129,7 @@ struct vc_model {
   float* vvec = nullptr; float vbias = 0.f;
   __half* vvec_h = nullptr;               // fp16 copy of vvec (bf16 mode, additive attention fast path)
   int attn_gate = 0;                      // VC_ATTN_GATE: CTAs per SM allowed in the v3 scoring phase at a time (0 = no gate; measured: no gain)
-  int attn_variant = 4;                   // VC_ATTN_VARIANT: 4 = tensor-core reductions (default), 3 = shuffle-reduction kernel
+  int attn_variant = 5;                   // VC_ATTN_VARIANT: 5 = persistent warp-specialised (default), 4 = one CTA per video (v4), 3 = shuffle-reduction kernel
   bool disable_attn_v3 = false;           // VC_DISABLE_ATTN_V3=1: generic attention kernel for the additive form (A/B testing)
   void* Wao = nullptr; float* bao = nullptr;
   void* dec_W[4] = {}; float* dec_bias[4] = {};
@@ -597,8 +597,9 @@ int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64
     case VC_ATTN_BAHDANAU:
     case VC_ATTN_LUONG_CONCAT: {
       if constexpr (!P) {
-        const bool use_mma = m->attn_variant == 4 && attn_additive_mma_ok(K, A, H, T) && ctx_ld % 8 == 0;
-        if (!m->disable_attn_v3 && (use_mma || attn_additive_fast_ok(K, A, H))) {
+        const bool use_mma = m->attn_variant >= 4 && attn_additive_mma_ok(K, A, H, T) && ctx_ld % 8 == 0;
+        const bool use_ws = m->attn_variant >= 5 && attn_additive_ws_ok(B, K, A, H, T, attn_out != nullptr) && ctx_ld % 8 == 0;
+        if (!m->disable_attn_v3 && (use_ws || use_mma || attn_additive_fast_ok(K, A, H))) {
           // queries leave the projection GEMM as fp16 and are consumed from registers by the v3 kernel
           __half* q16 = reinterpret_cast<__half*>(w.Q);
           {
@@ -612,6 +613,7 @@ int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64
           aa.sm_sem = m->attn_gate > 0 ? reinterpret_cast<int*>(w.flags) + 512 : nullptr;   // zeroed by run_decode
           aa.sem_limit = m->attn_gate;
           VC_SCOPE(VC_CLS_ATTN_STEP);
+          if (use_ws) return launch_attn_additive_ws(aa, K, s);
           if (use_mma) return launch_attn_additive_mma(aa, K, s);
           return launch_attn_additive(aa, K, s);
         }

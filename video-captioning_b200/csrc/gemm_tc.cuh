@@ -223,6 +223,16 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs g) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  // Weights never depend on the previous kernel: the producer starts the W loads of the first ring pass before the
+  // dependency wait (PDL, common.cuh); the A loads of those stages follow after it.
+  const int npre = nkb < kStages ? nkb : kStages;
+  if (threadIdx.x == 0) {
+    for (int kb = 0; kb < npre; ++kb) {
+      const uint32_t fb = smem_u32(&full_bar[kb]);
+      mbar_expect_tx(fb, kStageBytes);
+      tma_load_2d(smem_u32(smem + (size_t)kb * kStageBytes + kABytes), mapW, fb, kb * BK, n0);
+    }
+  }
   pdl_wait();                 // everything above overlaps the tail of the previous kernel in the stream
   pdl_launch_dependents();
 
@@ -241,14 +251,16 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs g) {
       }
       uint32_t stage = 0, phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_expect_tx(fb, kStageBytes);
+        if (kb >= npre) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          mbar_expect_tx(fb, kStageBytes);
+        }
         const int k = kb * BK;
         const int acol = g.a_col0[z] + k + (k >= g.a_split ? g.a_skip : 0);
         uint8_t* sa = smem + (size_t)stage * kStageBytes;
         tma_load_2d(smem_u32(sa), mapA, fb, acol, m0);
-        tma_load_2d(smem_u32(sa + kABytes), mapW, fb, k, n0);
+        if (kb >= npre) tma_load_2d(smem_u32(sa + kABytes), mapW, fb, k, n0);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -531,6 +543,17 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  // Weights never depend on the previous kernel: the producer starts the W loads of the first ring pass (first tile)
+  // before the dependency wait (PDL, common.cuh); the A loads of those stages follow after it.
+  const int npre = (t_first < t_last) ? (nkb < kStages ? nkb : kStages) : 0;
+  if (threadIdx.x == 0) {
+    const int n0 = (t_first % tiles_n) * BN;
+    for (int kb = 0; kb < npre; ++kb) {
+      const uint32_t fb = smem_u32(&full_bar[kb]);
+      mbar_expect_tx(fb, kStageBytes);
+      tma_load_2d(smem_u32(smem + (size_t)kb * kStageBytes + kABytes), mapW, fb, kb * BKE, n0);
+    }
+  }
   pdl_wait();                 // everything above overlaps the tail of the previous kernel in the stream
   pdl_launch_dependents();
 
@@ -542,14 +565,17 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
         const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const bool pre = (it == 0 && kb < npre);         // W already on its way, barrier already armed
           const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, kStageBytes);
+          if (!pre) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            mbar_expect_tx(fb, kStageBytes);
+          }
           const int k = kb * BKE;
           const int acol = g.a_col0[0] + k + (k >= g.a_split ? g.a_skip : 0);
           uint8_t* sa = smem + (size_t)stage * kStageBytes;
           tma_load_2d(smem_u32(sa), mapA, fb, acol, m0);
-          tma_load_2d(smem_u32(sa + kABytes), mapW, fb, k, n0);
+          if (!pre) tma_load_2d(smem_u32(sa + kABytes), mapW, fb, k, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (EPI == EPI_LSTM) {
