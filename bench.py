@@ -323,7 +323,13 @@ def main():
     if world > 1:
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / (float(ems.item()) * 1e-3)
-    e2e = {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": int(d2h)}
+    # bf16 mode: part of the batch is rounded to bf16 on the host cores and crosses the link at half the size
+    # (VideoCaptioningModel._generate_from_host_packed); the bytes are those of the last step's actual copies
+    h2d = int(getattr(model, "host_stats", {}).get("h2d_bytes", 0)) or int(host.numel() * 4)
+    e2e = {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+           "host_bytes_per_step": int(host.numel() * 4),
+           "ingest": ("fp32 host features; pieces go raw (fp32 H2D + device rounding) or host-packed to bf16 (host cores, "
+                      f"{getattr(model, 'host_pack_threads', 0)} threads), whichever route is free") if h2d != host.numel() * 4 else "fp32 H2D"}
 
     if rank != 0:
         if world > 1:

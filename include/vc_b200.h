@@ -32,6 +32,8 @@ enum { VC_ATTN_BAHDANAU = 0, VC_ATTN_LUONG_DOT = 1, VC_ATTN_LUONG_GENERAL = 2, V
  * bf16 operands / fp32 accumulation, fp32 cell state and logits */
 enum { VC_PREC_FP32 = 0, VC_PREC_BF16 = 1 };
 enum { VC_METHOD_GREEDY = 0, VC_METHOD_BEAM = 1 };
+/* element type of a feature buffer handed to vc_generate_ex */
+enum { VC_DTYPE_F32 = 0, VC_DTYPE_BF16 = 1 };
 
 /* Mirrors the config.model.* attributes the path reads (config/config.py:13-31). */
 typedef struct {
@@ -127,6 +129,19 @@ int vc_decode_beam(vc_model_t* m, int32_t B, int32_t T, const float* mask, const
 int vc_generate(vc_model_t* m, const float* feats, int32_t B, int32_t T, const int32_t* frame_lengths,
                 const float* mask, const vc_decode_params_t* p, int32_t* tokens, int32_t* lengths, float* scores,
                 float* attn_weights, void* workspace, size_t workspace_bytes, vc_stream_t stream);
+
+/* ---- feature ingest (predictor.py:101-107 `torch.FloatTensor(features).to(device)`: 1.3 MB of fp32 per video over
+ * PCIe is the end-to-end bottleneck).  bf16 mode rounds the features to bf16 before the first GEMM anyway, so a
+ * caller may do that rounding on the HOST for part of a batch and ship half the bytes:
+ *   vc_host_pack_bf16  host: dst[i] = bf16(src[i]), round to nearest even, on `threads` host threads (no CUDA call)
+ *   vc_convert_bf16    device: the same rounding for the part of the batch that crossed the link as fp32
+ *   vc_generate_ex     vc_generate with the feature element type stated (VC_DTYPE_BF16 only in VC_PREC_BF16 mode)
+ */
+int vc_host_pack_bf16(const float* src, uint16_t* dst, size_t n, int32_t threads);
+int vc_convert_bf16(const float* src_dev, void* dst_dev, int64_t n, vc_stream_t stream);
+int vc_generate_ex(vc_model_t* m, const void* feats, int32_t feats_dtype, int32_t B, int32_t T, const int32_t* frame_lengths,
+                   const float* mask, const vc_decode_params_t* p, int32_t* tokens, int32_t* lengths, float* scores,
+                   float* attn_weights, void* workspace, size_t workspace_bytes, vc_stream_t stream);
 
 /* ---- teacher-forced forward: VideoCaptioningModel.forward / CaptionDecoder.forward
  * (video_captioning_model.py:35-77, decoder.py:173-221).  input_tokens [B,L] int32;

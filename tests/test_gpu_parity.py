@@ -342,6 +342,38 @@ def test_host_feature_ingest_matches_device_path():
     assert torch.equal(c["generated_tokens"], m.generate(dev, START, END, max_length=9)["generated_tokens"])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("piece,threads", [(2, 1), (3, 4), (64, 2)])
+def test_host_packed_ingest_bf16(monkeypatch, piece, threads):
+    """bf16 mode, HOST fp32 features: pieces reach the device either as fp32 (+ device rounding) or rounded to bf16
+    on the host cores; either way every feature is rounded once to nearest even, so the result must equal the
+    device-resident call on the pre-rounded bf16 features bit for bit -- whatever the split, piece size, chunking
+    (ragged last chunk / piece), pinned or pageable memory -- and stay within the bf16 bar of the fp32-feature call."""
+    from oracle import synth
+    cfg = synth.make_config("tiny")
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, "bahdanau", seed=71, logit_gain=4.0, end_token_id=END, end_bias=0.3)
+    m = make_native_model(cfg, V, sd, "bahdanau", "bf16")
+    m.host_window_size = 14          # two windows (14 + 9 videos), three decode chunks each
+    m.host_chunk_fractions = (0.3, 0.7, 1.0)
+    m.host_piece_size = piece
+    m.host_pack_threads = threads
+    host = torch.from_numpy(synth.make_features(23, 16, 256, seed=72, kind="ragged")).pin_memory()
+    dev16 = host.cuda().to(torch.bfloat16)
+    for method, kw in (("greedy", {}), ("beam", {"beam_size": 3})):
+        a = m.generate(dev16, START, END, max_length=9, method=method, **kw)
+        for src in (host, host.clone()):
+            b = m.generate(src, START, END, max_length=9, method=method, **kw)
+            assert torch.equal(a["generated_tokens"], b["generated_tokens"])
+            if method == "beam":
+                assert torch.equal(a["lengths"], b["lengths"]) and torch.equal(a["scores"], b["scores"])
+    m.host_pack = False          # plain fp32 transfer (tf32 feature projection): same tokens up to near-ties
+    c = m.generate(host, START, END, max_length=9, method="greedy")["generated_tokens"]
+    a = m.generate(dev16, START, END, max_length=9, method="greedy")["generated_tokens"]
+    n = min(a.shape[1], c.shape[1])
+    assert (a[:, :n] == c[:, :n]).float().mean() > 0.9
+
+
 # ------------------------------------------------------------------ fused selection (vocab-GEMM statistics) == streaming selection
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,V,B,K", [("tiny", 1000, 9, 5), ("tiny", 2500, 5, 3), ("small", 10000, 6, 5),

@@ -119,3 +119,23 @@ def test_host_chunk_schedule_covers_batch():
             assert sp[0][0] == 0 and sp[-1][1] == B
             assert all(a[1] == b[0] for a, b in zip(sp, sp[1:]))
             assert all(0 < hi - lo <= chunk for lo, hi in sp)
+
+
+def test_host_pack_bf16_matches_round_to_nearest_even():
+    """vc_host_pack_bf16 (host cores, AVX-512 or scalar) == torch's fp32 -> bf16 rounding, incl. NaN / Inf / denormals,
+    odd lengths, unaligned starts and every thread count."""
+    import torch
+    from video_captioning_b200 import _native
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3 * 80 * 4096 + 37, generator=g) * 3
+    x[:6] = torch.tensor([float("nan"), float("inf"), -float("inf"), 1e-40, -0.0, 65504.0])
+    x[100:200] = torch.arange(100, dtype=torch.float32) * 0.0078125 + 1.0        # exact ties at the bf16 rounding point
+    ref = x.to(torch.bfloat16)
+    for threads in (1, 3, 16):
+        for off in (0, 1, 5):
+            src = x[off:].contiguous()
+            dst = torch.zeros(src.numel(), dtype=torch.bfloat16)
+            _native.host_pack_bf16(src, dst, threads)
+            a, b = dst.view(torch.int16), ref[off:].view(torch.int16)
+            nan = torch.isnan(src)
+            assert torch.equal(a[~nan], b[~nan]) and torch.isnan(dst[nan]).all()

@@ -34,7 +34,8 @@ PRECISION_IDS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 EXPORTED_SYMBOLS = (
     "vc_last_error", "vc_version", "vc_launch_count", "vc_profile_begin", "vc_profile_end", "vc_model_create", "vc_model_set_weight", "vc_model_finalize",
     "vc_model_destroy", "vc_workspace_bytes", "vc_encoder_forward", "vc_attn_precompute",
-    "vc_decode_greedy", "vc_decode_beam", "vc_generate", "vc_forward_teacher", "vc_linear",
+    "vc_decode_greedy", "vc_decode_beam", "vc_generate", "vc_generate_ex", "vc_host_pack_bf16", "vc_convert_bf16",
+    "vc_forward_teacher", "vc_linear",
     "vc_attention_step", "vc_beam_select",
 )
 
@@ -54,7 +55,8 @@ class DecodeParams(ctypes.Structure):
 
 def nvcc_command(out_path: str = LIB_PATH):
     return ["nvcc", "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-            "-shared", "-Xcompiler", "-fPIC", "-I", _INCLUDE, "-o", out_path, os.path.join(_CSRC, "capi.cu")]
+            "-shared", "-Xcompiler", "-fPIC", "-I", _INCLUDE, "-o", out_path, os.path.join(_CSRC, "capi.cu"),
+            os.path.join(_CSRC, "host_pack.cpp")]
 
 
 def _sources_mtime() -> float:
@@ -111,6 +113,10 @@ def load_library() -> ctypes.CDLL:
         lib.vc_decode_beam.argtypes = [vp, i32, i32, f32p, ctypes.POINTER(DecodeParams), i32p, i32p, f32p, vp, sz, vp]
         lib.vc_generate.argtypes = [vp, f32p, i32, i32, i32p, f32p, ctypes.POINTER(DecodeParams), i32p, i32p, f32p,
                                     f32p, vp, sz, vp]
+        lib.vc_generate_ex.argtypes = [vp, vp, i32, i32, i32, i32p, f32p, ctypes.POINTER(DecodeParams), i32p, i32p, f32p,
+                                       f32p, vp, sz, vp]
+        lib.vc_host_pack_bf16.argtypes = [vp, vp, sz, i32]
+        lib.vc_convert_bf16.argtypes = [f32p, vp, i64, vp]
         lib.vc_forward_teacher.argtypes = [vp, f32p, i32, i32, i32p, f32p, i32p, i32, f32p, f32p, f32p, vp, sz, vp]
         lib.vc_linear.argtypes = [i32, f32p, f32p, f32p, f32p, i32, i32, i32, i32, vp, sz, vp]
         lib.vc_attention_step.argtypes = [vp, f32p, f32p, f32p, i32, i32, i32, f32p, f32p, vp, sz, vp]
@@ -221,9 +227,12 @@ class NativeModel:
         return DecodeParams(METHOD_BEAM if method == "beam" else METHOD_GREEDY, int(K), int(S), int(start), int(end),
                             float(length_penalty), float(temperature), int(bool(diverse)))
 
-    def _prep_feats(self, feats):
+    def _prep_feats(self, feats, allow_bf16=False):
         require_cuda(feats, "video_features")
-        f = feats.detach().to(dtype=torch.float32).contiguous()
+        if allow_bf16 and feats.dtype == torch.bfloat16:
+            f = feats.detach().contiguous()      # host-packed ingest: already rounded (vc_generate_ex, VC_DTYPE_BF16)
+        else:
+            f = feats.detach().to(dtype=torch.float32).contiguous()
         if f.dim() != 3 or f.shape[2] != self.desc.feature_dim:
             raise ValueError(f"video_features must be [B,T,{self.desc.feature_dim}], got {tuple(f.shape)}")
         return f
@@ -253,7 +262,8 @@ class NativeModel:
 
     def generate(self, feats, start, end, max_length, mask=None, method="greedy", beam_size=5, length_penalty=1.0,
                  temperature=1.0, diverse=False, want_attention=True):
-        f = self._prep_feats(feats)
+        f = self._prep_feats(feats, allow_bf16=self.desc.precision == PREC_BF16)
+        dtype_id = 1 if f.dtype == torch.bfloat16 else 0
         B, T, _ = f.shape
         m, lengths = self._prep_mask(mask, B, T, self.device)
         S = int(max_length)
@@ -266,9 +276,9 @@ class NativeModel:
         attn = torch.empty(B, S, T, dtype=torch.float32, device=self.device) if (want_attention and not beam) else None
         with torch.cuda.device(self.device):
             ws = self._workspace(B, T, K, S)
-            check(self.lib.vc_generate(self._h, _ptr(f), B, T, _ptr(lengths), _ptr(m), ctypes.byref(p), _ptr(tokens),
-                                       _ptr(lens), _ptr(scores), _ptr(attn), _ptr(ws), ws.numel(),
-                                       _stream(self.device)), "vc_generate")
+            check(self.lib.vc_generate_ex(self._h, _ptr(f), dtype_id, B, T, _ptr(lengths), _ptr(m), ctypes.byref(p),
+                                          _ptr(tokens), _ptr(lens), _ptr(scores), _ptr(attn), _ptr(ws), ws.numel(),
+                                          _stream(self.device)), "vc_generate")
         return tokens, lens, scores, attn
 
     def forward_teacher(self, feats, input_tokens, mask=None, want_attention=True):
@@ -301,6 +311,28 @@ class NativeModel:
             check(self.lib.vc_attention_step(self._h, _ptr(e), _ptr(h), _ptr(m), B, T, K, _ptr(ctx), _ptr(w), _ptr(ws),
                                              ws.numel(), _stream(self.device)), "vc_attention_step")
         return ctx, w
+
+
+def host_pack_bf16(src: torch.Tensor, dst: torch.Tensor, threads: int) -> None:
+    """dst (host, bf16) = src (host, fp32) rounded to nearest even, on ``threads`` host threads (GIL released)."""
+    if src.device.type != "cpu" or dst.device.type != "cpu" or src.dtype != torch.float32 or dst.dtype != torch.bfloat16:
+        raise ValueError("host_pack_bf16: host fp32 source and host bf16 destination expected")
+    if not (src.is_contiguous() and dst.is_contiguous()) or src.numel() != dst.numel():
+        raise ValueError("host_pack_bf16: contiguous buffers of equal length expected")
+    check(load_library().vc_host_pack_bf16(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), src.numel(),
+                                           int(threads)), "vc_host_pack_bf16")
+
+
+def convert_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst (device, bf16) = src (device, fp32), round to nearest even, on the current stream."""
+    require_cuda(src, "src")
+    require_cuda(dst, "dst")
+    if src.dtype != torch.float32 or dst.dtype != torch.bfloat16 or src.numel() != dst.numel():
+        raise ValueError("convert_bf16: fp32 source and bf16 destination of equal length expected")
+    if not (src.is_contiguous() and dst.is_contiguous()):
+        raise ValueError("convert_bf16: contiguous buffers expected")
+    with torch.cuda.device(src.device):
+        check(load_library().vc_convert_bf16(_ptr(src), _ptr(dst), src.numel(), _stream(src.device)), "vc_convert_bf16")
 
 
 def linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, precision: str = "fp32",

@@ -832,6 +832,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -953,6 +956,14 @@ __global__ void __launch_bounds__(32 * (4 * NG + 4 * NCG + 1), 1) attn_additive_
         q_vi = vi;
       }
       if (has_next && vin != vi) load_q((int)blockIdx.x + vin * (int)gridDim.x, qb ^ 1);
+      if (sw == 0 && lane == 0 && u + 2 * NG < total) {
+        // the key tile of this group's unit after the next one -> L2 (one contiguous block of 16 frames): the
+        // register prefetch below then only has to cover the L2 latency, not HBM's
+        int vp = vin, fp = ftn + NG;
+        while (fp >= NT) { fp -= NT; ++vp; }
+        const int rows = T - fp * 16 < 16 ? T - fp * 16 : 16;
+        bulk_prefetch_l2(a.keys + ((int64_t)((int)blockIdx.x + vp * (int)gridDim.x) * T + fp * 16) * D, (uint32_t)(rows * D * 2));
+      }
       const __half* q = q_w + (size_t)qb * K * 128 + tg * 8;
       int t0 = ft * 16 + g, t1 = t0 + 8;
       t0 = t0 < T ? t0 : T - 1;

@@ -427,18 +427,29 @@ EpiStore<OutT, TANH, P> estore(OutT* C, int64_t ldc, const float* bias, float* C
 
 // ---------------------------------------------------------------- encoder  (encoder.py:52-98)
 template <class ActT>
-int run_encoder(vc_model* m, WS<ActT>& w, const float* feats, int B, int T, const int* lengths, float* enc_out_user,
-                float* final_user, cudaStream_t s) {
+int run_encoder(vc_model* m, WS<ActT>& w, const void* feats_any, int feats_dtype, int B, int T, const int* lengths,
+                float* enc_out_user, float* final_user, cudaStream_t s) {
   constexpr bool P = std::is_same<ActT, float>::value;
   const vc_model_desc_t& d = m->d;
   const int F = d.feature_dim, H = d.hidden_dim;
   const int BT = B * T;
+  const float* feats = reinterpret_cast<const float*>(feats_any);
   // feature projection (:70)
   bool proj_done = false;
+  if (feats_dtype == VC_DTYPE_BF16) {
+    // features already rounded to bf16 (host-packed ingest, vc_host_pack_bf16 / vc_convert_bf16): plain bf16 GEMM
+    VC_CHECK(!P, "bf16 features need the bf16 precision mode");
+    if constexpr (!P) {
+      VC_SCOPE(VC_CLS_ENC_FEATURE_PROJ);
+      VC_TRY((gemm<ActT>(gargs(feats_any, F, m->Wp, F, BT, H, F), F, estore<ActT, false, P>(w.proj, H, m->bp), s)));
+    }
+    proj_done = true;
+  }
   if constexpr (!P) {
+    if (proj_done) {
+    } else
     // bf16 mode: the tensor cores read the fp32 features (and the fp32 weight copy) as tf32 -- no conversion pass
-    auto it = m->raw.find("encoder.feature_projection.weight");
-    if (!m->disable_tf32_proj && it != m->raw.end() && H >= 256 && F % 32 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0) {
+    if (auto it = m->raw.find("encoder.feature_projection.weight"); !m->disable_tf32_proj && it != m->raw.end() && H >= 256 && F % 32 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0) {
       VC_SCOPE(VC_CLS_ENC_FEATURE_PROJ);
       VC_TRY(tc::launch_gemm_tc_tf32(gargs(feats, F, it->second.first, F, BT, H, F), F, estore<bf16, false, false>(w.proj, H, m->bp), s));
       proj_done = true;
@@ -939,18 +950,37 @@ size_t vc_workspace_bytes(const vc_model_t* m, int32_t B, int32_t T, int32_t K, 
 
 #define VC_DISPATCH(m, expr_f32, expr_bf16) ((m)->d.precision == VC_PREC_FP32 ? (expr_f32) : (expr_bf16))
 
-int vc_encoder_forward(vc_model_t* m, const float* feats, int32_t B, int32_t T, const int32_t* lengths, float* enc_out,
-                       float* enc_final, void* ws, size_t ws_bytes, vc_stream_t stream) {
+static int encoder_forward_typed(vc_model_t* m, const void* feats, int32_t feats_dtype, int32_t B, int32_t T, const int32_t* lengths,
+                                 float* enc_out, float* enc_final, void* ws, size_t ws_bytes, vc_stream_t stream) {
   VC_CHECK(m != nullptr && feats != nullptr, "null argument");
+  VC_CHECK(feats_dtype == VC_DTYPE_F32 || feats_dtype == VC_DTYPE_BF16, "unknown feature dtype %d", feats_dtype);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // the encoder part of the workspace does not depend on K/S; accept any workspace sized for K=1,S=1
   VC_TRY(check_common(m, B, T, 1, 1, ws_bytes, ws));
   if (m->d.precision == VC_PREC_FP32) {
     WS<float> w = carve<float>(m->d, ws, B, T, 1, 1);
-    return run_encoder<float>(m, w, feats, B, T, lengths, enc_out, enc_final, s);
+    return run_encoder<float>(m, w, feats, feats_dtype, B, T, lengths, enc_out, enc_final, s);
   }
   WS<bf16> w = carve<bf16>(m->d, ws, B, T, 1, 1);
-  return run_encoder<bf16>(m, w, feats, B, T, lengths, enc_out, enc_final, s);
+  return run_encoder<bf16>(m, w, feats, feats_dtype, B, T, lengths, enc_out, enc_final, s);
+}
+
+int vc_encoder_forward(vc_model_t* m, const float* feats, int32_t B, int32_t T, const int32_t* lengths, float* enc_out,
+                       float* enc_final, void* ws, size_t ws_bytes, vc_stream_t stream) {
+  return encoder_forward_typed(m, feats, VC_DTYPE_F32, B, T, lengths, enc_out, enc_final, ws, ws_bytes, stream);
+}
+
+// fp32 -> bf16 (round to nearest even) on the device: the raw part of a host-packed ingest batch
+int vc_convert_bf16(const float* src, void* dst, int64_t n, vc_stream_t stream) {
+  VC_CHECK(src != nullptr && dst != nullptr && n >= 0 && n % 4 == 0, "vc_convert_bf16: n must be a multiple of 4");
+  VC_CHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "vc_convert_bf16: unaligned buffers");
+  if (n == 0) return VC_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t n4 = n / 4;
+  VC_SCOPE(VC_CLS_CONVERT);
+  convert_f32_to_bf16_kernel<<<(int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16), 256, 0, s>>>(src, reinterpret_cast<bf16*>(dst), n4);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
 }
 
 int vc_attn_precompute(vc_model_t* m, int32_t B, int32_t T, void* ws, size_t ws_bytes, vc_stream_t stream) {
@@ -998,11 +1028,17 @@ int vc_decode_beam(vc_model_t* m, int32_t B, int32_t T, const float* mask, const
 int vc_generate(vc_model_t* m, const float* feats, int32_t B, int32_t T, const int32_t* frame_lengths, const float* mask,
                 const vc_decode_params_t* p, int32_t* tokens, int32_t* lengths, float* scores, float* attn, void* ws,
                 size_t ws_bytes, vc_stream_t stream) {
+  return vc_generate_ex(m, feats, VC_DTYPE_F32, B, T, frame_lengths, mask, p, tokens, lengths, scores, attn, ws, ws_bytes, stream);
+}
+
+int vc_generate_ex(vc_model_t* m, const void* feats, int32_t feats_dtype, int32_t B, int32_t T, const int32_t* frame_lengths,
+                   const float* mask, const vc_decode_params_t* p, int32_t* tokens, int32_t* lengths, float* scores, float* attn,
+                   void* ws, size_t ws_bytes, vc_stream_t stream) {
   VC_CHECK(m != nullptr && p != nullptr && feats != nullptr && tokens != nullptr, "null argument");
   VC_CHECK(p->method == VC_METHOD_GREEDY || p->method == VC_METHOD_BEAM, "Unsupported generation method: %d", p->method);
   const int K = p->method == VC_METHOD_BEAM ? p->beam_size : 1;
   VC_TRY(check_common(m, B, T, K, p->max_length, ws_bytes, ws));
-  VC_TRY(vc_encoder_forward(m, feats, B, T, frame_lengths, nullptr, nullptr, ws, ws_bytes, stream));
+  VC_TRY(encoder_forward_typed(m, feats, feats_dtype, B, T, frame_lengths, nullptr, nullptr, ws, ws_bytes, stream));
   VC_TRY(vc_attn_precompute(m, B, T, ws, ws_bytes, stream));
   if (p->method == VC_METHOD_GREEDY) return vc_decode_greedy(m, B, T, mask, p, tokens, attn, ws, ws_bytes, stream);
   VC_CHECK(lengths != nullptr, "beam decoding needs a lengths output");

@@ -16,6 +16,10 @@ Semantics kept on purpose (SURVEY.md sections 3.3, 8a):
 """
 from __future__ import annotations
 
+import collections
+import os
+import threading
+import time
 import weakref
 from typing import Dict, Optional
 
@@ -80,6 +84,17 @@ class VideoCaptioningModel(nn.Module):
         self.precision = precision
         self.chunk_size = int(chunk_size)  # videos per native call (bounds the workspace)
         self.host_chunk_size = 256         # videos per H2D chunk when the features live in host memory
+        # bf16 mode: part of a host batch is rounded to bf16 on the host cores and crosses PCIe at half the size
+        # (_generate_from_host_packed); VC_HOST_PACK=0 or host_pack=False keeps the plain fp32 transfer
+        self.host_pack = os.environ.get("VC_HOST_PACK", "1") != "0"
+        self.host_piece_size = int(os.environ.get("VC_HOST_PIECE", "64"))   # videos per transfer piece of the packed ingest
+        self.host_inflight = 3             # piece copies queued ahead on the copy stream
+        self.host_window_size = 1024       # videos staged on the device at a time (0.67 GB of bf16 at the MSVD shape)
+        self.host_chunk_fractions = tuple(float(x) for x in os.environ.get("VC_HOST_CHUNKS", "0.625,1.0").split(","))
+        self.host_pack_threads = int(os.environ.get("VC_HOST_PACK_THREADS", "0")) or max(
+            1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+        self._packed = None
+        self._packed_key = None
         self._copy_stream = None
         self._staging = None
         self._staging_key = None
@@ -137,7 +152,10 @@ class VideoCaptioningModel(nn.Module):
                                        beam_size=kwargs.get("beam_size", 5), length_penalty=kwargs.get("length_penalty", 1.0),
                                        temperature=kwargs.get("temperature", 1.0), diverse=kwargs.get("diverse_beams", False))
         if video_features.device.type == "cpu":
-            outs = self._generate_from_host(h, video_features, video_mask, gen)
+            if self.precision == "bf16" and self.host_pack and video_features.dtype == torch.float32 and video_features.dim() == 3:
+                outs = self._generate_from_host_packed(h, video_features.contiguous(), video_mask, gen)
+            else:
+                outs = self._generate_from_host(h, video_features, video_mask, gen)
         else:
             outs = []
             for lo in range(0, B, self.chunk_size):
@@ -197,6 +215,188 @@ class VideoCaptioningModel(nn.Module):
             outs.append(gen(self._staging[i % 2][: hi - lo], mk))
             free[i % 2].record(compute)
         return outs
+
+    def _generate_from_host_packed(self, h, feats: torch.Tensor, mask, gen):
+        """bf16-mode ingest of HOST fp32 features.  The PCIe link (54 GB/s, 1.3 MB per video) is the end-to-end
+        bottleneck and bf16 mode rounds the features to bf16 anyway, so the batch is cut into pieces of
+        ``host_piece_size`` videos that reach the device by one of two routes, whichever is free:
+          * raw    : fp32 piece -> H2D -> vc_convert_bf16 on the copy stream (the link's share)
+          * packed : vc_host_pack_bf16 on the host cores (a worker thread, GIL released) -> pinned bf16 -> H2D at half
+                     the bytes (the cores' share)
+        Within a chunk of ``host_chunk_size`` videos the copy loop takes raw pieces from the front and the packer takes
+        pieces from the back until they meet; every piece lands in one device bf16 buffer and the chunk is decoded as
+        soon as its pieces are in (vc_generate_ex, VC_DTYPE_BF16), while the next chunk is on its way.  All features are rounded exactly once, to nearest even, on
+        either route, so results do not depend on the split.  Rows are returned in input order."""
+        dev = h.device
+        B, T, F = feats.shape
+        piece = max(1, min(self.host_piece_size, self.chunk_size, B))
+        window = min(B, max(piece, min(self.chunk_size, self.host_window_size) // piece * piece))
+        compute = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        copy = self._copy_stream
+        key = (window, piece, T, F, str(dev))
+        if self._packed_key != key:
+            self._packed = dict(
+                dev16=torch.empty(window, T, F, dtype=torch.bfloat16, device=dev),
+                raw=[torch.empty(piece, T, F, dtype=torch.float32, device=dev) for _ in range(2)],
+                host16=[torch.empty(piece, T, F, dtype=torch.bfloat16).pin_memory() for _ in range(4)])
+            self._packed_key = key
+        st = self._packed
+        pinned = feats.is_pinned()
+        outs = {}
+        chunk_free = {}                      # chunk slot of the window -> event: its last decode has read dev16
+        raw_free = [None, None]
+        for w0 in range(0, B, window):
+            w1 = min(B, w0 + window)
+            chunks = self._packed_chunks(w0, w1, piece)
+            pieces, span, owner = [], [], []
+            for ci, (clo, chi) in enumerate(chunks):
+                first = len(pieces)
+                for lo in range(clo, chi, piece):
+                    pieces.append((lo, min(chi, lo + piece)))
+                    owner.append(ci)
+                span.append([first, len(pieces)])
+            left = [b - a for a, b in span]   # pieces of each chunk not yet enqueued
+            lock = threading.Lock()
+            # per chunk: [next raw piece (from its front), one past the last unclaimed piece (the packer takes from its
+            # back)]; both sides work on the earliest chunk that still has unclaimed pieces, so chunks complete -- and
+            # are decoded -- one after the other while the transfer of the later ones is still running
+
+            def claim(from_back):              # call with the lock held
+                for fb in span:
+                    if fb[0] < fb[1]:
+                        if from_back:
+                            fb[1] -= 1
+                            return fb[1]
+                        fb[0] += 1
+                        return fb[0] - 1
+                return None
+
+            ready = collections.deque()
+            have = threading.Semaphore(0)
+            bufs = collections.deque((b, None) for b in st["host16"])     # (pinned bf16 buffer, event of its last H2D)
+            buf_sem = threading.Semaphore(len(st["host16"]))
+            errors = []
+
+            def packer():
+                try:
+                    while True:
+                        buf_sem.acquire()          # a free pinned buffer first: a claimed piece is a commitment
+                        with lock:
+                            idx = claim(True)
+                        if idx is None:
+                            buf_sem.release()
+                            return
+                        with lock:
+                            buf, ev = bufs.popleft()
+                        if ev is not None:
+                            ev.synchronize()
+                        lo, hi = pieces[idx]
+                        t0 = time.perf_counter()
+                        _native.host_pack_bf16(feats[lo:hi], buf[: hi - lo], self.host_pack_threads)
+                        stats["pack_s"] += time.perf_counter() - t0
+                        stats["packed"] += 1
+                        with lock:
+                            ready.append((idx, buf))
+                        have.release()
+                except Exception as e:      # surfaced by the copy loop
+                    errors.append(e)
+                    have.release()
+
+            stats = dict(pack_s=0.0, packed=0, raw=0, sync_s=0.0, idle_s=0.0, h2d_bytes=0, t0=time.perf_counter())
+            if w0 > 0:                        # later windows of the same call accumulate
+                stats["h2d_bytes"] = self.host_stats.get("h2d_bytes", 0)
+            self.host_stats = stats
+            worker = threading.Thread(target=packer, daemon=True)
+            worker.start()
+            inflight = collections.deque()     # events of enqueued piece copies, oldest first
+            n_raw = 0
+            done = 0
+            while done < len(pieces):
+                if errors:
+                    raise errors[0]
+                item = None
+                with lock:
+                    if ready:
+                        item = ("packed",) + ready.popleft()
+                    else:
+                        idx = claim(False)
+                        if idx is not None:
+                            item = ("raw", idx, None)
+                if item is None:               # the packer holds the last pieces
+                    t0 = time.perf_counter()
+                    have.acquire()
+                    stats["idle_s"] += time.perf_counter() - t0
+                    continue
+                if item[0] == "packed":
+                    have.acquire(blocking=False)
+                kind, idx, buf = item
+                lo, hi = pieces[idx]
+                ci = owner[idx]
+                dst = st["dev16"][lo - w0: hi - w0]
+                with torch.cuda.stream(copy):
+                    if ci in chunk_free:
+                        copy.wait_event(chunk_free.pop(ci))
+                    stats["h2d_bytes"] += (hi - lo) * T * F * (2 if kind == "packed" else 4)
+                    if kind == "packed":
+                        dst.copy_(buf[: hi - lo], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy)
+                        with lock:
+                            bufs.append((buf, ev))
+                        buf_sem.release()
+                    else:
+                        slot = n_raw % 2
+                        n_raw += 1
+                        if raw_free[slot] is not None:
+                            copy.wait_event(raw_free[slot])
+                        src = feats[lo:hi]
+                        st["raw"][slot][: hi - lo].copy_(src, non_blocking=pinned)
+                        _native.convert_bf16(st["raw"][slot][: hi - lo], dst)
+                        raw_free[slot] = torch.cuda.Event()
+                        raw_free[slot].record(copy)
+                        ev = raw_free[slot]
+                    inflight.append(ev)
+                    left[ci] -= 1
+                    if left[ci] == 0:          # chunk complete: decode it
+                        rdy = torch.cuda.Event()
+                        rdy.record(copy)
+                        compute.wait_event(rdy)
+                        clo, chi = chunks[ci]
+                        mk = None if mask is None else mask[clo:chi].to(dev, non_blocking=True)
+                        with torch.cuda.stream(compute):
+                            outs[clo] = gen(st["dev16"][clo - w0: chi - w0], mk)
+                            fr = torch.cuda.Event()
+                            fr.record(compute)
+                        chunk_free[ci] = fr
+                done += 1
+                # pace the loop to the link: at most two piece copies queued, so that a piece packed meanwhile is
+                # sent instead of the next raw one
+                t0 = time.perf_counter()
+                while len(inflight) > self.host_inflight:
+                    inflight.popleft().synchronize()
+                stats["sync_s"] += time.perf_counter() - t0
+            worker.join()
+            stats["raw"] = n_raw
+            stats["loop_s"] = time.perf_counter() - stats.pop("t0")
+            if errors:
+                raise errors[0]
+        return [outs[k] for k in sorted(outs)]
+
+    def _packed_chunks(self, w0: int, w1: int, piece: int):
+        """Decode chunks of one window of the packed ingest.  A chunk's decode has a latency floor (160 dependent encoder
+        steps, 20 decode steps: ~4 ms however few videos it holds), so few large chunks beat many small ones; the last
+        chunk is the smaller one because its decode is the part of the step no transfer overlaps.  ``host_chunk_fractions``
+        are cumulative fractions of the window, rounded to whole pieces."""
+        n = w1 - w0
+        cuts = sorted({min(n, max(piece, int(round(f * n / piece)) * piece)) for f in self.host_chunk_fractions} | {n})
+        lo, out = 0, []
+        for c in cuts:
+            if c > lo:
+                out.append((w0 + lo, w0 + c))
+                lo = c
+        return out
 
     @staticmethod
     def _host_spans(B: int, chunk: int):
