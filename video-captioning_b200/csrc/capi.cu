@@ -116,6 +116,7 @@ struct vc_model {
   bool disable_persistent_lstm = false;   // VC_DISABLE_PERSISTENT_LSTM=1: per-timestep launches (A/B testing)
   bool disable_tf32_proj = false;         // VC_DISABLE_TF32_PROJ=1: convert the features to bf16 first (A/B testing)
   int dbg_vocab = 0;                      // VC_DEBUG_VOCAB: timing experiments (gemm_tc.cuh VocabStats::dbg), results invalid
+  bool disable_fused_reorder = true;      // VC_FUSED_REORDER=1: the fused selection kernel also does the reorder/embedding gather (measured slower than the separate PDL launch: 54 vs 33 + 20 us per step)
   bool disable_fused_select = false;      // VC_DISABLE_FUSED_SELECT=1: stream the whole logits row in the selection (A/B testing)
   // derived, operand-typed (float or bf16 according to d.precision)
   void* Wp = nullptr; float* bp = nullptr;
@@ -777,10 +778,16 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
     }
     // selection
     const int* parent = nullptr;
+    bool reorder_done = false;
     if (fused_sel) {
-      VC_SCOPE(VC_CLS_SELECT);
-      VC_TRY(launch_select_fused(bs, lg, ldl, w.vs_cmax, w.vs_part, 8 * vtn, 2 * vtn, B, K, V, S, step, p.end_token_id,
-                                 p.length_penalty, w.parent, w.cur_tok, mode == DM_GREEDY ? 1 : 0, tokens_out, s));
+      if constexpr (!P) {
+        // the selection kernel also gathers the parent rows' (h, c) and the next tokens' embeddings (reorder fused in)
+        VC_SCOPE(VC_CLS_SELECT);
+        VC_TRY(launch_select_fused(bs, lg, ldl, w.vs_cmax, w.vs_part, 8 * vtn, 2 * vtn, B, K, V, S, step, p.end_token_id,
+                                   p.length_penalty, w.parent, w.cur_tok, mode == DM_GREEDY ? 1 : 0, tokens_out, st,
+                                   (step + 1 < S && !m->disable_fused_reorder) ? 1 : 0, s));
+        reorder_done = !m->disable_fused_reorder;
+      }
       if (mode == DM_BEAM) parent = w.parent;
     } else if (mode == DM_GREEDY) {
       VC_SCOPE(VC_CLS_SELECT);
@@ -797,7 +804,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       set_tokens_kernel<<<(R + 127) / 128, 128, 0, s>>>(w.cur_tok, teacher_tokens, S, step + 1, R);
     }
     VC_CUDA(cudaGetLastError());
-    if (step + 1 < S) {
+    if (step + 1 < S && !reorder_done) {
       VC_SCOPE(VC_CLS_REORDER_EMBED);
       VC_CUDA(launch_pdl(reorder_embed_kernel<ActT>, dim3(R), dim3(128), 0, s, st, parent, (const int*)w.cur_tok, V));
     }
@@ -908,6 +915,8 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   m->disable_tf32_proj = env != nullptr && env[0] == '1';
   env = getenv("VC_DEBUG_VOCAB");
   m->dbg_vocab = env != nullptr ? atoi(env) : 0;
+  env = getenv("VC_FUSED_REORDER");
+  m->disable_fused_reorder = !(env != nullptr && env[0] == '1');
   env = getenv("VC_DISABLE_FUSED_SELECT");
   m->disable_fused_select = env != nullptr && env[0] == '1';
   *out = m;

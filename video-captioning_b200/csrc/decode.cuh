@@ -457,6 +457,32 @@ __global__ void __launch_bounds__(kSelWarps * 32) beam_select_kernel(
                          length_penalty, parent, cur_tok);
 }
 
+// One warp moves row r's next-step inputs into place: the parent row's new (h, c) of every layer into this row's
+// GEMM operands (video_captioning_model.py:247-249,269-272) and the embedding of the next token (decoder.py:130).
+template <class ActT>
+__device__ __forceinline__ void reorder_row_warp(const DecState<ActT>& st, int64_t r, int64_t p, int tok, int V, int lane) {
+  for (int l = 0; l < st.L; ++l) {
+    const ActT* hs = st.h_new[l] + p * st.H;
+    const float* cs = st.c_new[l] + p * st.H;
+    ActT* hd = st.x_rec[l] + r * st.x_ld[l];
+    float* cd = st.c[l] + r * st.H;
+    for (int u = lane * 4; u < st.H; u += 128) {
+      float hv[4];
+      load4(hs + u, hv);
+      store4(hd + u, hv);
+      *reinterpret_cast<float4*>(cd + u) = *reinterpret_cast<const float4*>(cs + u);
+    }
+  }
+  tok = min(max(tok, 0), V - 1);
+  const ActT* e = st.emb_table + (int64_t)tok * st.E;
+  ActT* ed = st.emb_dst + r * st.emb_ld;
+  for (int i = lane * 4; i < st.E; i += 128) {
+    float ev[4];
+    load4(e + i, ev);
+    store4(ed + i, ev);
+  }
+}
+
 // ---------------------------------------------------------------- fused selection from the vocab GEMM's statistics
 // bf16 mode.  The vocabulary GEMM's epilogue (gemm_tc.cuh, STATS) leaves, per row, the maximum of every
 // 32-column chunk of the logits and a (max, sum exp) pair per 128 columns.  Every element of a row's top-K
@@ -475,7 +501,8 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
                                                                  const float* cmax, const float2* part,
                                                                  int nc, int np, int B, int K, int V, int S, int step, int end_id,
                                                                  float length_penalty, int* __restrict__ parent,
-                                                                 int* __restrict__ cur_tok, int greedy, int* __restrict__ tokens_out) {
+                                                                 int* __restrict__ cur_tok, int greedy, int* __restrict__ tokens_out,
+                                                                 const DecState<bf16> st, int do_reorder) {
   __shared__ float s_cv[KMAX * KMAX];
   __shared__ int s_ci[KMAX * KMAX];
   __shared__ SelScratch scratch;
@@ -574,22 +601,28 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
     }
   }
   if (greedy) {
+    __syncwarp();
+    const int tok = s_ci[k * K];
     if (lane == 0) {
-      const int tok = s_ci[k * K];
       cur_tok[r] = tok;
       tokens_out[r * S + step] = tok;
     }
+    if (do_reorder) reorder_row_warp(st, r, r, tok, V, lane);
     return;
   }
   __syncthreads();
   if (k == 0) beam_select_video<(KMAX * KMAX + 31) / 32>(bs, s_cv, s_ci, scratch, b, K, V, S, step, end_id, length_penalty, parent, cur_tok);
+  if (!do_reorder) return;
+  // reorder fused into the selection: warp k moves row k of this video (parent / token were written by warp 0 above)
+  __syncthreads();
+  reorder_row_warp(st, r, (int64_t)parent[r], cur_tok[r], V, lane);
 }
 
 // host-side dispatch on (beam size, chunk count)
 inline int launch_select_fused(BeamState bs, const float* logits, int64_t ld, const float* cmax, const float2* part, int nc, int np,
                                int B, int K, int V, int S, int step, int end_id, float lp, int* parent, int* cur_tok, int greedy,
-                               int* tokens_out, cudaStream_t s) {
-#define VC_SEL(KM, CL) VC_CUDA(launch_pdl(select_fused_kernel<KM, CL>, dim3(B), dim3(K * 32), 0, s, bs, logits, ld, cmax, part, nc, np, B, K, V, S, step, end_id, lp, parent, cur_tok, greedy, tokens_out))
+                               int* tokens_out, const DecState<bf16>& st, int do_reorder, cudaStream_t s) {
+#define VC_SEL(KM, CL) VC_CUDA(launch_pdl(select_fused_kernel<KM, CL>, dim3(B), dim3(K * 32), 0, s, bs, logits, ld, cmax, part, nc, np, B, K, V, S, step, end_id, lp, parent, cur_tok, greedy, tokens_out, st, do_reorder))
 #define VC_SEL_K(CL)                     \
   do {                                   \
     if (K == 1) VC_SEL(1, CL);           \
