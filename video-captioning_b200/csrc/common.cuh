@@ -146,20 +146,33 @@ inline bool pdl_enabled() {
   return v == 1;
 }
 
+// cluster_x > 1: thread-block clusters of that many CTAs along x (grid.x must be a multiple of it)
 template <class... KArgs, class... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                                      Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  if (cluster_x > 1) {
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = (unsigned)cluster_x;
+    at[1].val.clusterDim.y = 1;
+    at[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  return launch_pdl_cluster(kern, grid, block, smem, stream, 1, static_cast<Args&&>(args)...);
 }
 
 }  // namespace vc

@@ -107,6 +107,64 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA pairs (thread-block clusters of 2, tcgen05 cta_group::2).  One 256x256 tile per pair: each CTA stages its own
+// 128 rows of A and HALF of the W tile (128 of its 256 rows), the leader CTA issues M=256 MMAs that read both CTAs' shared
+// memory and write each CTA's 128 accumulator rows into that CTA's TMEM.  A ring stage is 32 KB instead of 48 KB per 512
+// MMA cycles: 5 stages fit where 3 did, which is what these GEMMs were short of (bytes in flight = bandwidth x latency).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's leader CTA
+// TMA load whose completion bytes are counted on the LEADER CTA's barrier (executed by both CTAs of the pair)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+// completion of the pair's MMAs -> the same barrier in both CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -135,12 +193,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN.
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int bn, int m = BM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // kind::tf32 instruction descriptor: D=f32, A=B=tf32 (format code 2), both K-major, M=128, N=BN.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int bn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int bn, int m = BM) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // 16-byte chunk `c` (0..7) of row `r` inside a 128B-swizzled box
@@ -492,7 +550,11 @@ template <int EPI> struct PersistentCfg {
 // TF32: the operands in memory are fp32 (read by the tensor cores as tf32); a k-block is still 128 bytes per row,
 // i.e. 32 elements, and one MMA covers 8 of them.  Used for the feature projection so that the fp32 input
 // features are consumed as they are (no fp32 -> bf16 conversion pass over 1.3 MB per video).
-template <int kStages, int EPI, class OutT, bool TANH, bool STATS, bool TF32 = false>
+// MC: launched as clusters of 2 CTAs (cta_group::2, see the helpers above).  The pair works on the m-tiles (2i, 2i+1) of the
+// same n-tile; both producers signal the leader's full barrier, the leader's MMA completions release the ring slot and
+// publish the accumulator in both CTAs, and both epilogues hand the accumulator back on the leader's barrier
+// (maps.W[1]: W with a 128-row box).
+template <int kStages, int EPI, class OutT, bool TANH, bool STATS, bool TF32 = false, bool MC = false>
 __global__ void __launch_bounds__(PersistentCfg<EPI>::kThreads, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, const int tiles_m, const int tiles_n,
                           const VocabStats vstat) {
@@ -502,7 +564,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
   constexpr int BKE = TF32 ? 32 : BK;              // elements per k-block (128 bytes per row)
   constexpr int kEpiThreads = 32 * PersistentCfg<EPI>::kEpiWarps;
   constexpr uint32_t kABytes = BM * BK * 2;
-  constexpr uint32_t kBBytes = BN * BK * 2;
+  constexpr uint32_t kBBytes = (MC ? BN / 2 : BN) * BK * 2;  // the part of the W tile this CTA stages
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -516,12 +578,17 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
   const CUtensorMap* mapA = &maps.A[0];
   const CUtensorMap* mapW = &maps.W[0];
   const int nkb = g.K / BKE;
-  const int num_tiles = tiles_m * tiles_n;
+  // scheduling units: CTAs, or CTA pairs working on pairs of m-tiles (MC; tiles_m is even)
+  const int crank = MC ? (int)cluster_ctarank() : 0;
+  const int unit = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int units = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int kMT = MC ? 2 : 1;                  // m-tiles per scheduled tile
+  const int num_tiles = (tiles_m / kMT) * tiles_n;
   // tile schedule (m-major tile index, n fastest): round-robin, or contiguous ranges when the epilogue carries
   // per-row state from tile to tile (STATS)
-  const int t_first = STATS ? (int)((int64_t)blockIdx.x * num_tiles / gridDim.x) : (int)blockIdx.x;
-  const int t_last = STATS ? (int)((int64_t)(blockIdx.x + 1) * num_tiles / gridDim.x) : num_tiles;
-  const int t_step = STATS ? 1 : (int)gridDim.x;
+  const int t_first = STATS ? (int)((int64_t)unit * num_tiles / units) : unit;
+  const int t_last = STATS ? (int)((int64_t)(unit + 1) * num_tiles / units) : num_tiles;
+  const int t_step = STATS ? 1 : units;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -530,7 +597,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full[a]), 1);
-      mbar_init(smem_u32(&tmem_empty[a]), kEpiThreads);
+      mbar_init(smem_u32(&tmem_empty[a]), MC ? 2 * kEpiThreads : kEpiThreads);   // MC: both CTAs' epilogues, on the leader
     }
     mbar_init(smem_u32(&c_full), 1);
     mbar_init(smem_u32(&c_empty), 1);
@@ -538,11 +605,34 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
     asm volatile("prefetch.tensormap [%0];" ::"l"(mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(mapW) : "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  if (warp == 1) {
+    if (MC) tmem_alloc_2sm(smem_u32(&tmem_base_slot), 512);
+    else tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (MC) cluster_sync_all();      // the peer's barriers are initialised before anything is signalled on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  // operand tiles of a k-block -> ring slot.  MC: this CTA's half of the W tile, completion counted on the leader's barrier
+  auto load_w = [&](uint8_t* sb, uint32_t fb, int k, int n0) {
+    if (MC) tma_load_2d_2sm(smem_u32(sb), &maps.W[1], fb, k, n0 + crank * (BN / 2));
+    else tma_load_2d(smem_u32(sb), mapW, fb, k, n0);
+  };
+  auto load_a = [&](uint8_t* sa, uint32_t fb, int acol, int m0) {
+    if (MC) tma_load_2d_2sm(smem_u32(sa), mapA, fb, acol, m0);
+    else tma_load_2d(smem_u32(sa), mapA, fb, acol, m0);
+  };
+  // the barrier of a slot is armed once per use, by the leader, for both CTAs' bytes
+  auto arm = [&](uint32_t fb) {
+    if (!MC) mbar_expect_tx(fb, kStageBytes);
+    else if (crank == 0) mbar_expect_tx(fb, 2 * kStageBytes);
+  };
+  // an epilogue thread is done with accumulator a: tell the MMA issuer (MC: the leader's barrier, from either CTA)
+  auto arrive_tmem_empty = [&](uint32_t bar) {
+    if (MC && crank != 0) mbar_arrive_remote(bar, 0u);
+    else mbar_arrive_cta(bar);
+  };
   // Weights never depend on the previous kernel: the producer starts the W loads of the first ring pass (first tile)
   // before the dependency wait (PDL, common.cuh); the A loads of those stages follow after it.
   const int npre = (t_first < t_last) ? (nkb < kStages ? nkb : kStages) : 0;
@@ -550,8 +640,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
     const int n0 = (t_first % tiles_n) * BN;
     for (int kb = 0; kb < npre; ++kb) {
       const uint32_t fb = smem_u32(&full_bar[kb]);
-      mbar_expect_tx(fb, kStageBytes);
-      tma_load_2d(smem_u32(smem + (size_t)kb * kStageBytes + kABytes), mapW, fb, kb * BKE, n0);
+      arm(fb);
+      load_w(smem + (size_t)kb * kStageBytes + kABytes, fb, kb * BKE, n0);
     }
   }
   pdl_wait();                 // everything above overlaps the tail of the previous kernel in the stream
@@ -563,19 +653,19 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        const int m0 = ((tile / tiles_n) * kMT + crank) * BM, n0 = (tile % tiles_n) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           const bool pre = (it == 0 && kb < npre);         // W already on its way, barrier already armed
           const uint32_t fb = smem_u32(&full_bar[stage]);
           if (!pre) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            mbar_expect_tx(fb, kStageBytes);
+            arm(fb);
           }
           const int k = kb * BKE;
           const int acol = g.a_col0[0] + k + (k >= g.a_split ? g.a_skip : 0);
           uint8_t* sa = smem + (size_t)stage * kStageBytes;
-          tma_load_2d(smem_u32(sa), mapA, fb, acol, m0);
-          if (!pre) tma_load_2d(smem_u32(sa + kABytes), mapW, fb, k, n0);
+          load_a(sa, fb, acol, m0);
+          if (!pre) load_w(sa + kABytes, fb, k, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (EPI == EPI_LSTM) {
@@ -590,9 +680,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(BN) : make_idesc(BN);
+    if (lane == 0 && crank == 0) {
+      // ===== MMA issuer (MC: the pair's leader, M = 256 over both CTAs) =====
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(BN, MC ? 256 : BM) : make_idesc(BN, MC ? 256 : BM);
       uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
@@ -608,13 +698,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           const uint64_t db = make_smem_desc(smem_u32(sa + kABytes));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {      // 4 MMAs of 32 bytes of K each, either operand type
-            if (TF32) umma_tf32(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            else umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            if (MC && TF32) umma_tf32_2sm(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
+            else if (MC) umma_bf16_2sm(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
+            else if (TF32) umma_tf32(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
+            else umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
           }
-          umma_commit(smem_u32(&empty_bar[stage]));
+          if (MC) umma_commit_2sm(smem_u32(&empty_bar[stage]));     // slot free in both CTAs
+          else umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(&tmem_full[a]));
+        if (MC) umma_commit_2sm(smem_u32(&tmem_full[a]));           // accumulator halves complete in both CTAs
+        else umma_commit(smem_u32(&tmem_full[a]));
       }
     }
   } else {
@@ -635,7 +730,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       int cur_mb = -1;
       for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
         const int tmi = tile / tiles_n, tn = tile - tmi * tiles_n;
-        const int m0 = tmi * BM, n0 = tn * BN;
+        const int m0 = (tmi * kMT + crank) * BM, n0 = tn * BN;
         const int a = it & 1;
         if (tmi != cur_mb) {
           cur_mb = tmi;
@@ -749,7 +844,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           }
         }
         tc_fence_before();
-        mbar_arrive_cta(smem_u32(&tmem_empty[a]));
+        arrive_tmem_empty(smem_u32(&tmem_empty[a]));
         if (row < g.M && !(vstat.dbg & 4)) {
           *reinterpret_cast<float4*>(vstat.cmax + (size_t)row * vstat.nc + tn * 8 + half * 4) =
               make_float4(cm[0], cm[1], cm[2], cm[3]);
@@ -766,7 +861,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       constexpr int kBoxesPerHalf = (BN / 2) / kColsPerBox;   // 4 (fp32) or 2 (16-bit outputs)
       const uint32_t box_base = smem_u32(io_smem) + (uint32_t)(half * 2) * kBoxBytes;
       for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        const int m0 = ((tile / tiles_n) * kMT + crank) * BM, n0 = (tile % tiles_n) * BN;
         const int a = it & 1;
         float* bs = bias_s[a] + half * 128;
         {
@@ -809,7 +904,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           }
           if (bx == kBoxesPerHalf - 1) {                  // all TMEM reads of this accumulator half are done
             tc_fence_before();
-            mbar_arrive_cta(smem_u32(&tmem_empty[a]));
+            arrive_tmem_empty(smem_u32(&tmem_empty[a]));
           }
           fence_proxy_async_smem();
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -824,7 +919,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
     } else {
       const int et = threadIdx.x - 64;
       for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        const int m0 = ((tile / tiles_n) * kMT + crank) * BM, n0 = (tile % tiles_n) * BN;
         const int a = it & 1;
         float* bs = bias_s[a];
         for (int i = et; i < BN; i += 128) {
@@ -866,7 +961,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
                  pack_bf16(hn[6], hn[7]));
         }
         tc_fence_before();
-        mbar_arrive_cta(smem_u32(&tmem_empty[a]));
+        arrive_tmem_empty(smem_u32(&tmem_empty[a]));
         fence_proxy_async_smem();
         epi_bar_sync();
         if (et == 0) {
@@ -884,10 +979,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (MC) cluster_sync_all();      // neither CTA leaves while the peer may still signal its barriers / read its ring
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (MC) tmem_dealloc_2sm(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -1095,6 +1192,21 @@ inline bool tma_ok(const void* p, int64_t ld, int esize) {
   return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * esize) % 16 == 0;
 }
 
+// CTA-pair (cta_group::2) variant of the persistent kernel: even number of m-tiles and SMs, at least one pair-tile per pair.
+// VC_DISABLE_MC=1: single-CTA kernel everywhere (A/B).
+inline bool use_mc(int tm, int tn) {
+  static int en = -1;
+  if (en < 0) {
+    const char* e = getenv("VC_DISABLE_MC");
+    en = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return en == 1 && tm % 2 == 0 && num_sms() % 2 == 0 && (int64_t)(tm / 2) * tn >= num_sms() / 2;
+}
+// maps.W[1] <- the W operand with a 128-row box (each CTA of a pair stages half of the 256-row tile)
+inline int fill_w_half(TcMaps& mp, const GemmArgs& g, int esize) {
+  return get_map(&mp.W[1], g.W[0], (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, 128u, esize);
+}
+
 inline int fill_ab(TcMaps& mp, TcArgs& ta, const GemmArgs& g, int64_t a_cols, int BN, int esize = 2) {
   VC_CHECK(g.K % (128 / esize) == 0, "tensor-core GEMM needs K to be a multiple of %d (K=%d)", 128 / esize, g.K);
   VC_CHECK(g.N % 4 == 0, "bf16 tensor-core GEMM needs N %% 4 == 0 (N=%d)", g.N);
@@ -1150,7 +1262,12 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
     constexpr int kStages = 3;
     const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 4 * kBoxBytes + 1024;
     const int tm = (g.M + BM - 1) / BM, tn = (g.N + 255) / 256;
-    const int ctas = tm * tn < num_sms() ? tm * tn : num_sms();
+    // the vocabulary GEMM (stats) is paced by its epilogue, not by the operand ring: pairing only couples two epilogues
+    // (measured 72 vs 68 us); VC_MC_STATS=1 pairs it anyway
+    static const bool mc_stats = getenv("VC_MC_STATS") != nullptr && getenv("VC_MC_STATS")[0] == '1';
+    const bool mc = use_mc(tm, tn) && (stats == nullptr || mc_stats);
+    if (mc) VC_TRY(fill_w_half(mp, g, 2));
+    const int ctas = mc ? num_sms() : (tm * tn < num_sms() ? tm * tn : num_sms());
     VocabStats vs;
     memset(&vs, 0, sizeof(vs));
     if constexpr (sizeof(OutT) == 4 && !TANH) {
@@ -1162,16 +1279,32 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
         // no staging boxes: one 144-byte slot per epilogue thread for the sparse row-chunk stores
         constexpr int kStatStages = 3;
         const size_t smem_st = (size_t)kStatStages * (BM * BK * 2 + 256 * BK * 2) + 256 * 144 + 1024;
-        auto kern = gemm_tc_persistent_kernel<kStatStages, EPI_STORE, OutT, TANH, true>;
-        VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st));
-        VC_CUDA(launch_pdl(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem_st, stream, mp, ta, tm, tn, vs));
+        if (mc) {
+          constexpr int kMcStages = 5;     // 32 KB per stage
+          const size_t smem_mc = (size_t)kMcStages * (BM * BK * 2 + 128 * BK * 2) + 256 * 144 + 1024;
+          auto kern = gemm_tc_persistent_kernel<kMcStages, EPI_STORE, OutT, TANH, true, false, true>;
+          VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mc));
+          VC_CUDA(launch_pdl_cluster(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem_mc, stream, 2, mp, ta, tm, tn, vs));
+        } else {
+          auto kern = gemm_tc_persistent_kernel<kStatStages, EPI_STORE, OutT, TANH, true>;
+          VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st));
+          VC_CUDA(launch_pdl(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem_st, stream, mp, ta, tm, tn, vs));
+        }
         VC_CUDA(cudaGetLastError());
         return VC_OK;
       }
     }
-    auto kern = gemm_tc_persistent_kernel<kStages, EPI_STORE, OutT, TANH, false>;
-    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VC_CUDA(launch_pdl(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem, stream, mp, ta, tm, tn, vs));
+    if (mc) {
+      constexpr int kMcStages = 4;       // 32 KB per stage (5 would not fit beside the 64 KB of staging boxes)
+      const size_t smem_mc = (size_t)kMcStages * (BM * BK * 2 + 128 * BK * 2) + 4 * kBoxBytes + 1024;
+      auto kern = gemm_tc_persistent_kernel<kMcStages, EPI_STORE, OutT, TANH, false, false, true>;
+      VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mc));
+      VC_CUDA(launch_pdl_cluster(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem_mc, stream, 2, mp, ta, tm, tn, vs));
+    } else {
+      auto kern = gemm_tc_persistent_kernel<kStages, EPI_STORE, OutT, TANH, false>;
+      VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VC_CUDA(launch_pdl(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem, stream, mp, ta, tm, tn, vs));
+    }
   } else {
     // 3 stages x 32 KB: two CTAs co-reside per SM, so one CTA's epilogue overlaps the other's main loop
     constexpr int kStages = 3;
@@ -1199,12 +1332,22 @@ inline int launch_gemm_tc_tf32(const GemmArgs& g, int64_t a_cols, const EpiStore
   constexpr int kStages = 3;
   const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 4 * kBoxBytes + 1024;
   const int tm = (g.M + BM - 1) / BM, tn = (g.N + 255) / 256;
-  const int ctas = tm * tn < num_sms() ? tm * tn : num_sms();
+  const bool mc = use_mc(tm, tn);
+  if (mc) VC_TRY(fill_w_half(mp, g, 4));
+  const int ctas = mc ? num_sms() : (tm * tn < num_sms() ? tm * tn : num_sms());
   VocabStats vs;
   memset(&vs, 0, sizeof(vs));
-  auto kern = gemm_tc_persistent_kernel<kStages, EPI_STORE, bf16, false, false, true>;
-  VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VC_CUDA(launch_pdl(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem, stream, mp, ta, tm, tn, vs));
+  if (mc) {
+    constexpr int kMcStages = 4;
+    const size_t smem_mc = (size_t)kMcStages * (BM * BK * 2 + 128 * BK * 2) + 4 * kBoxBytes + 1024;
+    auto kern = gemm_tc_persistent_kernel<kMcStages, EPI_STORE, bf16, false, false, true, true>;
+    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mc));
+    VC_CUDA(launch_pdl_cluster(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem_mc, stream, 2, mp, ta, tm, tn, vs));
+  } else {
+    auto kern = gemm_tc_persistent_kernel<kStages, EPI_STORE, bf16, false, false, true>;
+    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VC_CUDA(launch_pdl(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem, stream, mp, ta, tm, tn, vs));
+  }
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -1242,11 +1385,20 @@ inline int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiLstm<bf16,
   if (!has_add && g.nz == 1 && (int)(grid.x * grid.y) >= num_sms()) {
     constexpr int kStages = 3;
     const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 3 * kBoxBytes + 1024;
-    auto kern = gemm_tc_persistent_kernel<kStages, EPI_LSTM, bf16, false, false>;
-    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VocabStats vs;
     memset(&vs, 0, sizeof(vs));
-    VC_CUDA(launch_pdl(kern, dim3(num_sms()), dim3(PersistentCfg<EPI_LSTM>::kThreads), smem, stream, mp, ta, (int)grid.y, (int)grid.x, vs));
+    if (use_mc((int)grid.y, (int)grid.x)) {
+      VC_TRY(fill_w_half(mp, g, 2));
+      constexpr int kMcStages = 5;
+      const size_t smem_mc = (size_t)kMcStages * (BM * BK * 2 + 128 * BK * 2) + 3 * kBoxBytes + 1024;
+      auto kern = gemm_tc_persistent_kernel<kMcStages, EPI_LSTM, bf16, false, false, false, true>;
+      VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mc));
+      VC_CUDA(launch_pdl_cluster(kern, dim3(num_sms()), dim3(PersistentCfg<EPI_LSTM>::kThreads), smem_mc, stream, 2, mp, ta, (int)grid.y, (int)grid.x, vs));
+    } else {
+      auto kern = gemm_tc_persistent_kernel<kStages, EPI_LSTM, bf16, false, false>;
+      VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VC_CUDA(launch_pdl(kern, dim3(num_sms()), dim3(PersistentCfg<EPI_LSTM>::kThreads), smem, stream, mp, ta, (int)grid.y, (int)grid.x, vs));
+    }
     VC_CUDA(cudaGetLastError());
     return VC_OK;
   }
