@@ -117,6 +117,7 @@ struct vc_model {
   bool disable_tf32_proj = false;         // VC_DISABLE_TF32_PROJ=1: convert the features to bf16 first (A/B testing)
   int dbg_vocab = 0;                      // VC_DEBUG_VOCAB: timing experiments (gemm_tc.cuh VocabStats::dbg), results invalid
   bool disable_fused_reorder = true;      // VC_FUSED_REORDER=1: the fused selection kernel also does the reorder/embedding gather (measured slower than the separate PDL launch: 54 vs 33 + 20 us per step)
+  bool disable_shared_thr = false;        // VC_DISABLE_SHARED_THR=1: per-CTA pruning thresholds only in the vocab GEMM (A/B testing)
   bool disable_fused_select = false;      // VC_DISABLE_FUSED_SELECT=1: stream the whole logits row in the selection (A/B testing)
   // derived, operand-typed (float or bf16 according to d.precision)
   void* Wp = nullptr; float* bp = nullptr;
@@ -332,6 +333,7 @@ struct WS {
   float *C[4], *Cn[4], *Q, *logits, *cand_val, *scores, *best_score;
   float* vs_cmax;        // vocab GEMM statistics (gemm_tc.cuh VocabStats): [R, nc] chunk maxima
   float2* vs_part;       // [R, np] log-sum-exp partials
+  int* vs_rowthr;        // [R] shared pruning threshold of a row (ordered-int key of a float), reset by the selection kernel
   int *cand_idx, *parent, *cur_tok, *done, *best_len, *best_seq, *hist[2];
   unsigned char* alive;
   size_t total;
@@ -373,6 +375,7 @@ WS<ActT> carve(const vc_model_desc_t& d, void* base, int B, int T, int K, int S)
     const size_t tn = (V + 255) / 256;
     w.vs_cmax = c.take<float>(R * 8 * tn);
     w.vs_part = c.take<float2>(R * 2 * tn);
+    w.vs_rowthr = c.take<int>(R);
   }
   w.cand_val = c.take<float>(R * K);
   w.cand_idx = c.take<int>(R * K);
@@ -702,6 +705,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
   bs.best_seq = w.best_seq; bs.hist[0] = w.hist[0]; bs.hist[1] = w.hist[1];
 
   VC_CUDA(cudaMemsetAsync(w.flags + 512, 0, sizeof(unsigned int) * 512, s));   // attention scoring-gate counters (per SM)
+  if (w.vs_rowthr != nullptr) VC_CUDA(cudaMemsetAsync(w.vs_rowthr, 0x80, sizeof(int) * (size_t)R, s));   // key of a very negative float
   {
     VC_SCOPE(VC_CLS_MISC);
     decode_init_kernel<ActT><<<R, 128, 0, s>>>(st, w.final_f32, R, K, p.start_token_id,
@@ -766,6 +770,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
           tc::VocabStats vs;
           memset(&vs, 0, sizeof(vs));
           vs.cmax = w.vs_cmax; vs.part = w.vs_part; vs.nc = 8 * vtn; vs.np = 2 * vtn;
+          vs.rowthr = m->disable_shared_thr ? nullptr : w.vs_rowthr;
           vs.dbg = m->dbg_vocab;
           vs.topk = K <= 8 ? K : 0;     // chunks that cannot be among the row's K best are never written
           VC_TRY(gemm_vocab_stats(gargs(w.O, H, m->Wv, H, R, V, H), H, estore<float, false, false>(lg, ldl, m->bv), s, vs));
@@ -784,7 +789,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
         // the selection kernel also gathers the parent rows' (h, c) and the next tokens' embeddings (reorder fused in)
         VC_SCOPE(VC_CLS_SELECT);
         VC_TRY(launch_select_fused(bs, lg, ldl, w.vs_cmax, w.vs_part, 8 * vtn, 2 * vtn, B, K, V, S, step, p.end_token_id,
-                                   p.length_penalty, w.parent, w.cur_tok, mode == DM_GREEDY ? 1 : 0, tokens_out, st,
+                                   p.length_penalty, w.parent, w.cur_tok, mode == DM_GREEDY ? 1 : 0, tokens_out, w.vs_rowthr, st,
                                    (step + 1 < S && !m->disable_fused_reorder) ? 1 : 0, s));
         reorder_done = !m->disable_fused_reorder;
       }
@@ -917,6 +922,8 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   m->dbg_vocab = env != nullptr ? atoi(env) : 0;
   env = getenv("VC_FUSED_REORDER");
   m->disable_fused_reorder = !(env != nullptr && env[0] == '1');
+  env = getenv("VC_DISABLE_SHARED_THR");
+  m->disable_shared_thr = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_FUSED_SELECT");
   m->disable_fused_select = env != nullptr && env[0] == '1';
   *out = m;

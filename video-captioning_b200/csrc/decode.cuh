@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
                                                                  int nc, int np, int B, int K, int V, int S, int step, int end_id,
                                                                  float length_penalty, int* __restrict__ parent,
                                                                  int* __restrict__ cur_tok, int greedy, int* __restrict__ tokens_out,
-                                                                 const DecState<bf16> st, int do_reorder) {
+                                                                 int* __restrict__ rowthr, const DecState<bf16> st, int do_reorder) {
   __shared__ float s_cv[KMAX * KMAX];
   __shared__ int s_ci[KMAX * KMAX];
   __shared__ SelScratch scratch;
@@ -512,6 +512,7 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
   constexpr float kL2e = 1.4426950408889634f;
   pdl_wait();                 // logits / cmax / part come from the vocabulary GEMM just before (read with ld.cg: PDL, common.cuh)
   pdl_launch_dependents();
+  if (lane == 0 && rowthr != nullptr) rowthr[r] = (int)0x80808080;     // the GEMM's shared pruning threshold of this row, for the next step
 
   // chunk maxima first (the longest dependent chain starts here)
   float cv[MAXCL];
@@ -621,8 +622,8 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
 // host-side dispatch on (beam size, chunk count)
 inline int launch_select_fused(BeamState bs, const float* logits, int64_t ld, const float* cmax, const float2* part, int nc, int np,
                                int B, int K, int V, int S, int step, int end_id, float lp, int* parent, int* cur_tok, int greedy,
-                               int* tokens_out, const DecState<bf16>& st, int do_reorder, cudaStream_t s) {
-#define VC_SEL(KM, CL) VC_CUDA(launch_pdl(select_fused_kernel<KM, CL>, dim3(B), dim3(K * 32), 0, s, bs, logits, ld, cmax, part, nc, np, B, K, V, S, step, end_id, lp, parent, cur_tok, greedy, tokens_out, st, do_reorder))
+                               int* tokens_out, int* rowthr, const DecState<bf16>& st, int do_reorder, cudaStream_t s) {
+#define VC_SEL(KM, CL) VC_CUDA(launch_pdl(select_fused_kernel<KM, CL>, dim3(B), dim3(K * 32), 0, s, bs, logits, ld, cmax, part, nc, np, B, K, V, S, step, end_id, lp, parent, cur_tok, greedy, tokens_out, rowthr, st, do_reorder))
 #define VC_SEL_K(CL)                     \
   do {                                   \
     if (K == 1) VC_SEL(1, CL);           \

@@ -514,8 +514,19 @@ struct VocabStats {
   float* logits;    // [M, ld] fp32, sparsely written (see above)
   int64_t ld;
   int topk;         // 1..8: prune; 0: store every chunk
+  int* rowthr;      // [M] or nullptr: pruning threshold shared by all CTAs (and both column halves) working on a row: the
+                    // largest "topk-th best chunk maximum" any of them has seen, as an ordered-int key; a chunk whose
+                    // maximum is strictly below it cannot be among the row's topk best chunks.  The caller presets it to a
+                    // very negative key before every launch.
   int dbg;          // timing experiments only (VC_DEBUG_VOCAB): 1 = skip the logits stores, 2 = skip the exp sums, 4 = skip stats stores
 };
+
+// monotonic float <-> int key (total order of the finite floats and infinities): atomicMax on keys == max on floats
+__device__ __forceinline__ int f2key(float x) {
+  const int b = __float_as_int(x);
+  return b >= 0 ? b : (b ^ 0x7fffffff);
+}
+__device__ __forceinline__ float key2f(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
 
 constexpr float kLog2e = 1.4426950408889634f;
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -743,12 +754,17 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           const int col = n0 + half * 128 + eh;
           bs[eh] = (g.bias[0] != nullptr && col < g.N) ? g.bias[0][col] : 0.f;
         }
+        const int row = m0 + r;
+        // threshold published by the other CTAs / the other column half working on this row (strictly-below test);
+        // read before the wait for the accumulator so that its latency is hidden
+        const bool shared_thr = vstat.rowthr != nullptr && vstat.topk > 0 && row < g.M;
+        const float gthr = shared_thr ? key2f(__ldcg(vstat.rowthr + row)) : -INFINITY;
+        const float thr_in = thr;
         mbar_wait(smem_u32(&tmem_full[a]), (uint32_t)((it >> 1) & 1));
         tc_fence_after();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // bias of this half staged
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + half * 128);
         const bool tail_tile = n0 + BN > g.N;
-        const int row = m0 + r;
         float run_m = -1e30f, run_s = 0.f;                // online (max, sum 2^((x-max) log2e)) of this half tile
         float cm[4];
         // TMEM loads are software-pipelined: the load of chunk bx+1 is in flight while chunk bx is processed
@@ -802,7 +818,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
             run_s += s0 + s1;
           }
           bool keep = false;
-          if (bm > thr && !(vstat.dbg & 1)) {
+          if (bm > thr && !(bm < gthr) && !(vstat.dbg & 1)) {
             if (vstat.topk > 0) {
               // sorted insert (descending; an equal earlier chunk stays ahead), then refresh the threshold
 #pragma unroll
@@ -845,6 +861,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         }
         tc_fence_before();
         arrive_tmem_empty(smem_u32(&tmem_empty[a]));
+        if (shared_thr && thr > thr_in && thr > gthr) atomicMax(vstat.rowthr + row, f2key(thr));
         if (row < g.M && !(vstat.dbg & 4)) {
           *reinterpret_cast<float4*>(vstat.cmax + (size_t)row * vstat.nc + tn * 8 + half * 4) =
               make_float4(cm[0], cm[1], cm[2], cm[3]);
