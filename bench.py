@@ -57,6 +57,20 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, source="fallback")
 
 
+def load_traffic(workload, B):
+    """Per-launch DRAM bytes of the kernel classes from the newest committed ncu full capture (profiles/*_traffic.json);
+    only valid for the workload and batch it was captured on (the default one)."""
+    import glob
+    if workload != DEFAULT_WORKLOAD or B != WORKLOADS[DEFAULT_WORKLOAD]["B"]:
+        return None
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None
+    d = json.load(open(files[-1]))
+    d["file"] = os.path.relpath(files[-1], ROOT)
+    return d
+
+
 # ---------------------------------------------------------------------------- algorithmic work per kernel class
 def class_work(wl, cfgm, B):
     """Algorithmic FLOPs and HBM bytes per STEP (whole batch) for each kernel class.
@@ -104,9 +118,18 @@ def class_work(wl, cfgm, B):
         by += R * kin * b + 4 * H * kin * b + 2 * R * H * b + 2 * R * H * 4
     w["dec_lstm"] = dict(flops=S * fl, bytes=S * by)
     w["dec_context_proj"] = dict(flops=S * 2 * R * (2 * H + E) * H, bytes=S * (R * (2 * H + E) * b + (2 * H + E) * H * b + R * H * b))
-    # logits are materialised in fp32 by this version (written by the GEMM, read by select)
-    w["dec_vocab"] = dict(flops=S * 2 * R * H * V, bytes=S * (R * H * b + V * H * b + R * V * 4))
-    w["select"] = dict(flops=0, bytes=S * R * V * 4)
+    tn = (V + 255) // 256
+    if wl["precision"] == "bf16" and V >= 256 and 8 * tn <= 1024:
+        # fused selection: the GEMM emits per-row chunk maxima (8 per 256-column tile) and
+        # log-sum-exp partials (2 float2 per tile) and only the >= K chunks of 128 bytes that can reach the top-K;
+        # the selection reads the statistics and K chunks per row
+        stats = R * (8 * tn + 2 * 2 * tn) * 4
+        w["dec_vocab"] = dict(flops=S * 2 * R * H * V, bytes=S * (R * H * b + V * H * b + stats + R * K * 128))
+        w["select"] = dict(flops=0, bytes=S * (stats + R * K * 128))
+    else:
+        # logits materialised in fp32 (written by the GEMM, read by the streaming selection)
+        w["dec_vocab"] = dict(flops=S * 2 * R * H * V, bytes=S * (R * H * b + V * H * b + R * V * 4))
+        w["select"] = dict(flops=0, bytes=S * R * V * 4)
     w["reorder_embed"] = dict(flops=0, bytes=(S - 1) * R * (Ld * (2 * H * b + 2 * H * 4) + 2 * E * b))
     w["misc"] = dict(flops=0, bytes=0)
     return w
@@ -369,6 +392,19 @@ def main():
                 "avg_launch_ms": d["ms_per_step"] / per_launch, "bytes_per_launch": work[dom]["bytes"] / per_launch}
     roof["peak_source"] = peaks["source"]
     roof["share_of_step"] = d["share"]
+    # DRAM traffic of that kernel per launch, from the committed ncu --set full capture of this workload (profiles/)
+    tr = load_traffic(args.workload, B)
+    if tr is not None and dom in tr["classes"]:
+        roof["traffic"] = tr["classes"][dom]["dram_bytes_per_launch"]
+        roof["traffic_source"] = tr["file"]
+    if "tanh" in work.get(dom, {}):
+        # Bahdanau scoring is bound by the special-function pipe (16 tanh / clk / SM, measured with scratch/mufu_bench.cu),
+        # not by HBM: report that roofline as well
+        sm_hz = (clocks or {}).get("sm_mhz", 1965.0) * 1e6
+        xu_peak = 16.0 * torch.cuda.get_device_properties(dev).multi_processor_count * sm_hz
+        ach = work[dom]["tanh"] / (d["ms_per_step"] * 1e-3)
+        roof["xu"] = {"bound": "mufu", "achieved": ach, "peak": xu_peak, "unit": "tanh/s", "frac": ach / xu_peak,
+                      "note": "peak = 16 MUFU results/clk/SM x SMs x sampled SM clock"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
