@@ -374,6 +374,39 @@ def test_host_packed_ingest_bf16(monkeypatch, piece, threads):
     assert (a[:, :n] == c[:, :n]).float().mean() > 0.9
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_replay_equals_plain_launches(precision):
+    """A generate() call whose arguments repeat (same tensors, same shapes) is captured as a CUDA graph on its second
+    occurrence and replayed afterwards: tokens / lengths / scores / attention weights must equal the plain-launch call,
+    new input data in the same buffer must be picked up, and the launch counter must keep counting."""
+    from oracle import synth
+    from video_captioning_b200 import _native
+    cfg = synth.make_config("tiny")
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, "bahdanau", seed=11, logit_gain=4.0, end_token_id=END, end_bias=0.3)
+    m = make_native_model(cfg, V, sd, "bahdanau", precision)
+    x = torch.from_numpy(synth.make_features(9, 16, 256, seed=12)).cuda()
+    y = torch.from_numpy(synth.make_features(9, 16, 256, seed=13)).cuda()
+    for method, kw in (("greedy", {}), ("beam", {"beam_size": 3})):
+        ref_x = m.generate(x.clone(), START, END, max_length=9, method=method, **kw)      # fresh buffers: plain launches
+        ref_y = m.generate(y.clone(), START, END, max_length=9, method=method, **kw)
+        buf = x.clone()
+        outs = []
+        for i in range(4):                                   # call 1 plain, call 2 captures, calls 3-4 replay
+            c0 = _native.launch_count()
+            outs.append(m.generate(buf, START, END, max_length=9, method=method, **kw))
+            assert _native.launch_count() > c0
+        buf.copy_(y)                                         # same buffer, new data
+        outs_y = m.generate(buf, START, END, max_length=9, method=method, **kw)
+        for o in outs:
+            for k in ref_x:
+                assert torch.equal(o[k], ref_x[k]), (method, k)
+        for k in ref_y:
+            assert torch.equal(outs_y[k], ref_y[k]), (method, k)
+    assert len(m._handle()._graphs) >= 1 or not m._handle()._graphs_on
+
+
 # ------------------------------------------------------------------ fused selection (vocab-GEMM statistics) == streaming selection
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,V,B,K", [("tiny", 1000, 9, 5), ("tiny", 2500, 5, 3), ("small", 10000, 6, 5),

@@ -134,16 +134,25 @@ KERNEL_CLASSES = ("convert", "enc_feature_proj", "enc_input_proj", "enc_recurren
                   "dec_context_proj", "dec_vocab", "select", "reorder_embed", "misc")
 
 
+_replayed_launches = 0     # kernel launches executed through CUDA-graph replays (the library counts at enqueue time)
+_profiling = False         # per-class event timing needs the plain launch path
+
+
 def launch_count() -> int:
-    return int(load_library().vc_launch_count())
+    """Kernel launches of this package executed so far (plain launches + launches inside replayed CUDA graphs)."""
+    return int(load_library().vc_launch_count()) + _replayed_launches
 
 
 def profile_begin() -> None:
+    global _profiling
+    _profiling = True
     check(load_library().vc_profile_begin(), "vc_profile_begin")
 
 
 def profile_end() -> Dict[str, Dict[str, float]]:
     """-> {class: {"ms": summed device milliseconds, "scopes": event-bracketed launch scopes}}"""
+    global _profiling
+    _profiling = False
     n = len(KERNEL_CLASSES)
     ms = (ctypes.c_float * n)()
     cnt = (ctypes.c_int32 * n)()
@@ -195,6 +204,9 @@ class NativeModel:
             check(self.lib.vc_model_finalize(self._h, st), "vc_model_finalize")
             torch.cuda.current_stream(self.device).synchronize()
         self._ws: Optional[torch.Tensor] = None
+        self._graphs_on = os.environ.get("VC_CUDA_GRAPHS", "1") != "0"
+        self._graphs: Dict[tuple, tuple] = {}
+        self._graph_seen: Dict[tuple, int] = {}
 
     def __del__(self):
         try:
@@ -219,6 +231,8 @@ class NativeModel:
     def _workspace(self, B, T, K, S) -> torch.Tensor:
         need = self.workspace_bytes(B, T, K, S)
         if self._ws is None or self._ws.numel() < need:
+            self._graphs.clear()                  # captured graphs point into the old workspace
+            self._graph_seen.clear()
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
@@ -270,16 +284,60 @@ class NativeModel:
         beam = method == "beam"
         K = int(beam_size) if beam else 1
         p = self._params(method, K, S, start, end, length_penalty, temperature, diverse)
-        tokens = torch.empty(B, S + 1 if beam else S, dtype=torch.int32, device=self.device)
-        lens = torch.empty(B, dtype=torch.int32, device=self.device) if beam else None
-        scores = torch.empty(B, dtype=torch.float32, device=self.device) if beam else None
-        attn = torch.empty(B, S, T, dtype=torch.float32, device=self.device) if (want_attention and not beam) else None
-        with torch.cuda.device(self.device):
-            ws = self._workspace(B, T, K, S)
+
+        def alloc():
+            return (torch.empty(B, S + 1 if beam else S, dtype=torch.int32, device=self.device),
+                    torch.empty(B, dtype=torch.int32, device=self.device) if beam else None,
+                    torch.empty(B, dtype=torch.float32, device=self.device) if beam else None,
+                    torch.empty(B, S, T, dtype=torch.float32, device=self.device) if (want_attention and not beam) else None)
+
+        def launch(outs, ws):
+            tokens, lens, scores, attn = outs
             check(self.lib.vc_generate_ex(self._h, _ptr(f), dtype_id, B, T, _ptr(lengths), _ptr(m), ctypes.byref(p),
                                           _ptr(tokens), _ptr(lens), _ptr(scores), _ptr(attn), _ptr(ws), ws.numel(),
                                           _stream(self.device)), "vc_generate")
-        return tokens, lens, scores, attn
+
+        with torch.cuda.device(self.device):
+            ws = self._workspace(B, T, K, S)
+            # The whole call is ~850 dependent launches: on small batches the host cannot enqueue them as fast as the
+            # GPU runs them.  A call whose arguments (shapes AND buffer addresses) repeat is captured once as a CUDA graph
+            # and replayed; the replay writes into the graph's own output buffers, which are cloned for the caller.
+            key = None
+            if self._graphs_on and not _profiling and m is None and f.data_ptr() == feats.data_ptr():
+                key = (f.data_ptr(), dtype_id, B, T, K, S, method, int(start), int(end), float(length_penalty),
+                       float(temperature), bool(diverse), bool(want_attention), ws.data_ptr(), ws.numel())
+            ent = self._graphs.get(key) if key is not None else None
+            global _replayed_launches
+            if ent is not None:
+                ent[0].replay()
+                _replayed_launches += ent[4]
+                return tuple(None if t is None else t.clone() for t in ent[1])
+            if key is not None:
+                if len(self._graph_seen) > 256:
+                    self._graph_seen.clear()
+                seen = self._graph_seen.get(key, 0) + 1
+                self._graph_seen[key] = seen
+                if seen >= 2:                      # second identical call: worth capturing
+                    outs = alloc()
+                    try:
+                        g = torch.cuda.CUDAGraph()
+                        n0 = int(self.lib.vc_launch_count())
+                        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                            launch(outs, ws)
+                        n_launch = int(self.lib.vc_launch_count()) - n0      # counted once, at capture, for this call
+                        if len(self._graphs) >= 16:
+                            self._graphs.pop(next(iter(self._graphs)))
+                        self._graphs[key] = (g, outs, f, ws, n_launch)     # keeps the captured buffers alive
+                        g.replay()
+                        return tuple(None if t is None else t.clone() for t in outs)
+                    except Exception:
+                        # capture not possible here (e.g. a launch attribute the driver cannot record): plain launches
+                        self._graphs_on = False
+                        self._graphs.clear()
+                        torch.cuda.synchronize(self.device)
+            outs = alloc()
+            launch(outs, ws)
+        return outs
 
     def forward_teacher(self, feats, input_tokens, mask=None, want_attention=True):
         f = self._prep_feats(feats)
