@@ -8,15 +8,15 @@ sd = synth.make_state_dict(cfg, V, "bahdanau", seed=0)
 m = vc.VideoCaptioningModel(cfg, V, precision="bf16", chunk_size=1024)
 m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m = m.cuda().eval()
 host = torch.randn(1024, 80, 4096).pin_memory()
-for label, setup in (("default", {}), ("threads8", dict(host_pack_threads=8)), ("threads14", dict(host_pack_threads=14)),
-                     ("inflight2", dict(host_inflight=2)), ("c50", dict(host_chunk_fractions=(0.5, 1.0))), ("c75", dict(host_chunk_fractions=(0.75, 1.0))), ("c1", dict(host_chunk_fractions=(1.0,))), ("c3", dict(host_chunk_fractions=(0.375, 0.75, 1.0))),
-                     ("nopack", dict(host_pack=False))):
+for label, setup in (("default", {}), ("c3", dict(host_chunk_fractions=(0.375, 0.75, 1.0))), ("c4", dict(host_chunk_fractions=(0.25, 0.5, 0.75, 1.0))),
+                     ("c3b", dict(host_chunk_fractions=(0.5, 0.8, 1.0))), ("c4b", dict(host_chunk_fractions=(0.4, 0.7, 0.9, 1.0))),
+                     ("c2b", dict(host_chunk_fractions=(0.75, 1.0))), ("default2", {}), ("nopack", dict(host_pack=False))):
     m.host_pack_threads = 16; m.host_inflight = 3; m.host_chunk_fractions = (0.625, 1.0); m.host_pack = True
     for k, v in setup.items(): setattr(m, k, v)
     for _ in range(2):
         o = m.generate(host, 1, 2, max_length=20, method="beam", beam_size=5); o["generated_tokens"].cpu()
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    n = 4
+    n = 8
     for _ in range(n):
         o = m.generate(host, 1, 2, max_length=20, method="beam", beam_size=5); o["generated_tokens"].cpu()
     dt = (time.perf_counter() - t0) / n

@@ -125,6 +125,23 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// monotonic float <-> int key (total order of the finite floats and infinities): integer max on keys == max on floats
+__device__ __forceinline__ int f2key(float x) {
+  const int b = __float_as_int(x);
+  return b >= 0 ? b : (b ^ 0x7fffffff);
+}
+__device__ __forceinline__ float key2f(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
+
+// Warp arg-max in the order (value descending, index ascending) with two REDUX instructions instead of a five-stage
+// shuffle butterfly.  Lanes without a candidate pass valid = false; if no lane has one, wi = 0x7fffffff.
+// (v + 0.0f turns -0.0 into +0.0 so that the key order agrees with the float comparison.)
+__device__ __forceinline__ void warp_argmax(bool valid, float v, int idx, float& wv, int& wi) {
+  const int key = valid ? f2key(v + 0.0f) : (int)0x80000000;
+  const int kmax = __reduce_max_sync(0xffffffffu, key);
+  wi = __reduce_min_sync(0xffffffffu, (valid && key == kmax) ? idx : 0x7fffffff);
+  wv = (wi == 0x7fffffff) ? -INFINITY : key2f(kmax);
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)

@@ -376,14 +376,9 @@ __device__ __forceinline__ void beam_select_video(const BeamState& bs, const flo
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
       if (cf[q] != 0x7fffffff && (bq < 0 || cv[q] > bv || (cv[q] == bv && cf[q] < bf))) { bv = cv[q]; bf = cf[q]; bq = q; }
-    float wv = bv;
-    int wf = bf;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float tv = __shfl_xor_sync(0xffffffffu, wv, o);
-      const int tf = __shfl_xor_sync(0xffffffffu, wf, o);
-      if (tf != 0x7fffffff && (wf == 0x7fffffff || tv > wv || (tv == wv && tf < wf))) { wv = tv; wf = tf; }
-    }
+    float wv;
+    int wf;
+    warp_argmax(bq >= 0, bv, bf, wv, wf);
     if (wf == 0x7fffffff) break;            // no live candidate left (warp-uniform)
     if (bq >= 0 && bf == wf) {              // flat indices are unique: exactly one owner
 #pragma unroll
@@ -426,12 +421,28 @@ __device__ __forceinline__ void beam_select_video(const BeamState& bs, const flo
     for (int i = lane; i < step; i += 32) bs.best_seq[(int64_t)b * S + i] = hin[(int64_t)(r0 + best_pk) * S + i];
     if (lane == 0) bs.best_seq[(int64_t)b * S + step] = sm.misc[2];
   }
+  // token histories of the kept beams: all loads first, then the stores (hin / hout may alias for the compiler, and a
+  // load -> store -> load chain per beam costs one memory round trip each)
+  for (int i0 = 0; i0 < step; i0 += 32) {
+    const int i = i0 + lane;
+    int hv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      hv[k] = 0;
+      if (k < K && i < step) {
+        const int src = (k < n_alive) ? r0 + sm.np[k] : r0 + k;
+        hv[k] = hin[(int64_t)src * S + i];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < K && i < step) hout[(int64_t)(r0 + k) * S + i] = hv[k];
+  }
   for (int k = 0; k < K; ++k) {
     const int r = r0 + k;
     const bool live = k < n_alive;
     const int src = live ? r0 + sm.np[k] : r;         // dead slot: keeps computing on benign inputs
     const int tok = live ? sm.tk[k] : end_id;
-    for (int i = lane; i < step; i += 32) hout[(int64_t)r * S + i] = hin[(int64_t)src * S + i];
     if (lane == 0) {
       hout[(int64_t)r * S + step] = tok;
       bs.scores[r] = live ? sm.ns[k] : -INFINITY;
@@ -557,14 +568,9 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
 #pragma unroll
       for (int i = 0; i < MAXCL; ++i)
         if (cv[i] > bv) { bv = cv[i]; bi = lane + 32 * i; }     // ascending i: the first maximum has the lowest chunk index
-      float wv = bv;
-      int wi = bi;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float tv = __shfl_xor_sync(0xffffffffu, wv, o);
-        const int ti = __shfl_xor_sync(0xffffffffu, wi, o);
-        if (tv > wv || (tv == wv && ti < wi)) { wv = tv; wi = ti; }
-      }
+      float wv;
+      int wi;
+      warp_argmax(bi != 0x7fffffff, bv, bi, wv, wi);
 #pragma unroll
       for (int i = 0; i < MAXCL; ++i)
         if (lane + 32 * i == wi) cv[i] = -INFINITY;
@@ -584,14 +590,9 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
 #pragma unroll
       for (int sel = 0; sel < KMAX; ++sel)
         if (val[sel] > bv || (val[sel] == bv && val[sel] != -INFINITY && cidx[sel] < bi)) { bv = val[sel]; bi = cidx[sel]; }
-      float wv = bv;
-      int wi = bi;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float tv = __shfl_xor_sync(0xffffffffu, wv, o);
-        const int ti = __shfl_xor_sync(0xffffffffu, wi, o);
-        if (tv > wv || (tv == wv && ti < wi)) { wv = tv; wi = ti; }
-      }
+      float wv;
+      int wi;
+      warp_argmax(bi != 0x7fffffff, bv, bi, wv, wi);
 #pragma unroll
       for (int sel = 0; sel < KMAX; ++sel)
         if (cidx[sel] == wi) val[sel] = -INFINITY;

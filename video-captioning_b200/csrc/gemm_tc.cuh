@@ -521,13 +521,6 @@ struct VocabStats {
   int dbg;          // timing experiments only (VC_DEBUG_VOCAB): 1 = skip the logits stores, 2 = skip the exp sums, 4 = skip stats stores
 };
 
-// monotonic float <-> int key (total order of the finite floats and infinities): atomicMax on keys == max on floats
-__device__ __forceinline__ int f2key(float x) {
-  const int b = __float_as_int(x);
-  return b >= 0 ? b : (b ^ 0x7fffffff);
-}
-__device__ __forceinline__ float key2f(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
-
 constexpr float kLog2e = 1.4426950408889634f;
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
