@@ -117,6 +117,7 @@ struct vc_model {
   bool disable_tf32_proj = false;         // VC_DISABLE_TF32_PROJ=1: convert the features to bf16 first (A/B testing)
   int dbg_vocab = 0;                      // VC_DEBUG_VOCAB: timing experiments (gemm_tc.cuh VocabStats::dbg), results invalid
   bool disable_fused_reorder = true;      // VC_FUSED_REORDER=1: the fused selection kernel also does the reorder/embedding gather (measured slower than the separate PDL launch: 54 vs 33 + 20 us per step)
+  bool disable_layer_sync = false;        // VC_DISABLE_LAYER_SYNC=1: stacked decoder LSTM GEMMs in plain stream order (A/B testing)
   bool disable_shared_thr = false;        // VC_DISABLE_SHARED_THR=1: per-CTA pruning thresholds only in the vocab GEMM (A/B testing)
   bool disable_fused_select = false;      // VC_DISABLE_FUSED_SELECT=1: stream the whole logits row in the selection (A/B testing)
   // derived, operand-typed (float or bf16 according to d.precision)
@@ -333,6 +334,7 @@ struct WS {
   float *C[4], *Cn[4], *Q, *logits, *cand_val, *scores, *best_score;
   float* vs_cmax;        // vocab GEMM statistics (gemm_tc.cuh VocabStats): [R, nc] chunk maxima
   float2* vs_part;       // [R, np] log-sum-exp partials
+  unsigned int* dec_sync; // [dec_layers][ceil(R/128)] tile-level hand-over counters between stacked decoder LSTM GEMMs
   int* vs_rowthr;        // [R] shared pruning threshold of a row (ordered-int key of a float), reset by the selection kernel
   int *cand_idx, *parent, *cur_tok, *done, *best_len, *best_seq, *hist[2];
   unsigned char* alive;
@@ -376,6 +378,7 @@ WS<ActT> carve(const vc_model_desc_t& d, void* base, int B, int T, int K, int S)
     w.vs_cmax = c.take<float>(R * 8 * tn);
     w.vs_part = c.take<float2>(R * 2 * tn);
     w.vs_rowthr = c.take<int>(R);
+    w.dec_sync = c.take<unsigned int>((size_t)d.dec_layers * ((R + 127) / 128));
   }
   w.cand_val = c.take<float>(R * K);
   w.cand_idx = c.take<int>(R * K);
@@ -706,6 +709,14 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
 
   VC_CUDA(cudaMemsetAsync(w.flags + 512, 0, sizeof(unsigned int) * 512, s));   // attention scoring-gate counters (per SM)
   if (w.vs_rowthr != nullptr) VC_CUDA(cudaMemsetAsync(w.vs_rowthr, 0x80, sizeof(int) * (size_t)R, s));   // key of a very negative float
+  // Stacked decoder LSTM GEMMs hand their h rows over tile by tile instead of kernel by kernel: layer l+1 starts on the SMs
+  // layer l's last (partial) tile round leaves idle.  Counters grow monotonically over the steps (no reset inside the loop).
+  unsigned int sync_arr = 0;
+  const int sync_rows = (R + 127) / 128;
+  if constexpr (!P) {
+    if (L > 1 && !m->disable_layer_sync && w.dec_sync != nullptr) sync_arr = tc::lstm_sync_arrivals(R, 4 * H);
+    if (sync_arr) VC_CUDA(cudaMemsetAsync(w.dec_sync, 0, sizeof(unsigned int) * (size_t)L * sync_rows, s));
+  }
   {
     VC_SCOPE(VC_CLS_MISC);
     decode_init_kernel<ActT><<<R, 128, 0, s>>>(st, w.final_f32, R, K, p.start_token_id,
@@ -744,6 +755,11 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
         e.h1_origin = w.Z; e.h1_origin_cols = ZW;
       }
       e.c_origin_in = w.C[l]; e.c_origin_out = w.Cn[l]; e.c_tma_cols = H;
+      if (sync_arr) {
+        e.sync_signal = (l < L - 1) ? w.dec_sync + (size_t)l * sync_rows : nullptr;
+        e.sync_wait = (l > 0) ? w.dec_sync + (size_t)(l - 1) * sync_rows : nullptr;
+        e.sync_target = sync_arr * (unsigned int)(step + 1);
+      }
       VC_SCOPE(VC_CLS_DEC_LSTM);
       VC_TRY((gemm<ActT>(g, lda, e, s)));
     }
@@ -922,6 +938,8 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   m->dbg_vocab = env != nullptr ? atoi(env) : 0;
   env = getenv("VC_FUSED_REORDER");
   m->disable_fused_reorder = !(env != nullptr && env[0] == '1');
+  env = getenv("VC_DISABLE_LAYER_SYNC");
+  m->disable_layer_sync = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_SHARED_THR");
   m->disable_shared_thr = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_FUSED_SELECT");

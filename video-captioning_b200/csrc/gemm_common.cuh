@@ -77,6 +77,14 @@ struct EpiLstm {
   const void* c_origin_in; const void* c_origin_out; int64_t c_tma_cols;
   const void* h0_origin; int64_t h0_origin_cols;
   const void* h1_origin; int64_t h1_origin_cols;
+  // Tile-level hand-over between two stacked LSTM GEMMs (persistent tensor-core kernel only, see gemm_tc.cuh):
+  // sync_signal[mt] is incremented once per finished (m-tile row mt, n-tile, CTA) after the h/c stores are globally
+  // visible; a kernel given sync_wait does NOT wait for the previous grid as a whole but, per m-tile row, until
+  // sync_wait[mt] >= sync_target.  Both nullptr: plain stream order.
+  unsigned int* sync_signal;
+  const unsigned int* sync_wait;
+  unsigned int sync_per_row;     // out: arrivals per m-tile row and launch (filled by the launcher)
+  unsigned int sync_target;      // in: value sync_wait[mt] must reach
 
   __device__ __forceinline__ void operator()(int z, int row, int col, float (&v)[4]) const {
     const int u = col >> 2;

@@ -165,6 +165,11 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(rank) : "memory");
 }
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -235,6 +240,10 @@ struct TcArgs {
   const float* bias[2];
   int io_col0[5][2];      // column offset of the tile origin inside each io map, per z
   int has_h1;
+  // tile-level hand-over between stacked LSTM GEMMs (EpiLstm::sync_*): counters per scheduled m-tile row
+  unsigned int* sync_signal;
+  const unsigned int* sync_wait;
+  unsigned int sync_target;
 };
 
 // ---------------------------------------------------------------- the kernel
@@ -648,7 +657,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       load_w(smem + (size_t)kb * kStageBytes + kABytes, fb, kb * BKE, n0);
     }
   }
-  pdl_wait();                 // everything above overlaps the tail of the previous kernel in the stream
+  // everything above overlaps the tail of the previous kernel in the stream.  A kernel that is handed its A rows tile by
+  // tile (sync_wait, below) does not wait for the previous grid as a whole: everything else it reads is older.
+  if (g.sync_wait == nullptr) pdl_wait();
   pdl_launch_dependents();
 
   if (warp == 0) {
@@ -658,6 +669,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       int it = 0;
       for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
         const int m0 = ((tile / tiles_n) * kMT + crank) * BM, n0 = (tile % tiles_n) * BN;
+        if (EPI == EPI_LSTM && g.sync_wait != nullptr) {
+          // the previous layer's GEMM (still running) publishes its h rows per m-tile row: acquire them
+          const unsigned int* flag = g.sync_wait + tile / tiles_n;
+          uint32_t spin = 0;
+          while (ld_acquire_gpu_u32(flag) < g.sync_target) {
+            if (++spin > (1u << 26)) {
+              printf("vc::tc layer hand-over timeout (block %d tile %d)\n", blockIdx.x, tile);
+              __trap();
+            }
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");   // order the acquire before the async-proxy loads
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           const bool pre = (it == 0 && kb < npre);         // W already on its way, barrier already armed
           const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -983,6 +1006,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           tma_store_commit();
           tma_store_wait_read();
           mbar_arrive_cta(smem_u32(&c_empty));          // c / h boxes may be refilled for the next tile
+          if (g.sync_signal != nullptr) {
+            // publish this tile's h rows to the next layer's GEMM: stores complete, then a release increment
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __threadfence();
+            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(g.sync_signal + tile / tiles_n), "r"(1u) : "memory");
+          }
         }
         epi_bar_sync();                                 // nobody rewrites h_box before the stores have read it
       }
@@ -1212,6 +1242,13 @@ inline bool use_mc(int tm, int tn) {
   }
   return en == 1 && tm % 2 == 0 && num_sms() % 2 == 0 && (int64_t)(tm / 2) * tn >= num_sms() / 2;
 }
+// Arrivals per scheduled m-tile row and launch of the persistent LSTM GEMM's tile-level hand-over (EpiLstm::sync_*), or 0
+// when a decoder-form LSTM GEMM of this shape does not take the persistent path (then stacked layers use stream order).
+inline unsigned int lstm_sync_arrivals(int M, int N) {
+  const int tm = (M + BM - 1) / BM, tn = N / 256;
+  if (N % 256 != 0 || tm * tn < num_sms()) return 0u;
+  return use_mc(tm, tn) ? 2u * (unsigned)tn : (unsigned)tn;
+}
 // maps.W[1] <- the W operand with a 128-row box (each CTA of a pair stages half of the 256-row tile)
 inline int fill_w_half(TcMaps& mp, const GemmArgs& g, int esize) {
   return get_map(&mp.W[1], g.W[0], (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, 128u, esize);
@@ -1397,6 +1434,9 @@ inline int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiLstm<bf16,
     const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 3 * kBoxBytes + 1024;
     VocabStats vs;
     memset(&vs, 0, sizeof(vs));
+    ta.sync_signal = e.sync_signal;
+    ta.sync_wait = e.sync_wait;
+    ta.sync_target = e.sync_target;
     if (use_mc((int)grid.y, (int)grid.x)) {
       VC_TRY(fill_w_half(mp, g, 2));
       constexpr int kMcStages = 5;

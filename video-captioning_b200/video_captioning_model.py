@@ -249,6 +249,10 @@ class VideoCaptioningModel(nn.Module):
         raw_free = [None, None]
         for w0 in range(0, B, window):
             w1 = min(B, w0 + window)
+            # the device buffer is reused by every window (and call): its previous readers -- all decodes enqueued so far --
+            # must be done before the first piece of this window lands (chunk boundaries differ between windows)
+            copy.wait_stream(compute)
+            chunk_free.clear()
             chunks = self._packed_chunks(w0, w1, piece)
             pieces, span, owner = [], [], []
             for ci, (clo, chi) in enumerate(chunks):
