@@ -117,6 +117,7 @@ struct vc_model {
   bool disable_tf32_proj = false;         // VC_DISABLE_TF32_PROJ=1: convert the features to bf16 first (A/B testing)
   int dbg_vocab = 0;                      // VC_DEBUG_VOCAB: timing experiments (gemm_tc.cuh VocabStats::dbg), results invalid
   bool disable_fused_reorder = true;      // VC_FUSED_REORDER=1: the fused selection kernel also does the reorder/embedding gather (measured slower than the separate PDL launch: 54 vs 33 + 20 us per step)
+  bool disable_ctx_handover = false;      // VC_DISABLE_CTX_HANDOVER=1: the context projection waits for the last LSTM GEMM as a whole (A/B testing)
   bool disable_layer_sync = false;        // VC_DISABLE_LAYER_SYNC=1: stacked decoder LSTM GEMMs in plain stream order (A/B testing)
   bool disable_shared_thr = false;        // VC_DISABLE_SHARED_THR=1: per-CTA pruning thresholds only in the vocab GEMM (A/B testing)
   bool disable_fused_select = false;      // VC_DISABLE_FUSED_SELECT=1: stream the whole logits row in the selection (A/B testing)
@@ -756,7 +757,8 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       }
       e.c_origin_in = w.C[l]; e.c_origin_out = w.Cn[l]; e.c_tma_cols = H;
       if (sync_arr) {
-        e.sync_signal = (l < L - 1) ? w.dec_sync + (size_t)l * sync_rows : nullptr;
+        // (the last layer hands over to the context projection)
+        e.sync_signal = (l < L - 1 || !m->disable_ctx_handover) ? w.dec_sync + (size_t)l * sync_rows : nullptr;
         e.sync_wait = (l > 0) ? w.dec_sync + (size_t)(l - 1) * sync_rows : nullptr;
         e.sync_target = sync_arr * (unsigned int)(step + 1);
       }
@@ -768,6 +770,12 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       GemmArgs g = gargs(w.Z, ZW, m->Wc, 2 * H + E, R, H, 2 * H + E);
       g.a_split = E + H;
       g.a_skip = H;
+      if (sync_arr && !m->disable_ctx_handover && tc::ctx_handover_ok(R, H)) {
+        // rows of h_top are taken over from the last LSTM layer's GEMM tile row by tile row (128x128-tile kernel only)
+        g.sync_wait = w.dec_sync + (size_t)(L - 1) * sync_rows;
+        g.sync_target = sync_arr * (unsigned int)(step + 1);
+        g.sync_row_shift = tc::lstm_sync_row_shift(R, 4 * H);
+      }
       VC_SCOPE(VC_CLS_DEC_CONTEXT_PROJ);
       VC_TRY((gemm<ActT>(g, ZW, estore<ActT, true, P>(w.O, H, m->bc), s)));
     }
@@ -938,6 +946,8 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   m->dbg_vocab = env != nullptr ? atoi(env) : 0;
   env = getenv("VC_FUSED_REORDER");
   m->disable_fused_reorder = !(env != nullptr && env[0] == '1');
+  env = getenv("VC_DISABLE_CTX_HANDOVER");
+  m->disable_ctx_handover = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_LAYER_SYNC");
   m->disable_layer_sync = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_SHARED_THR");

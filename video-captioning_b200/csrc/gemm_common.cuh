@@ -23,6 +23,12 @@ struct GemmArgs {
   // and spans a_origin_cols columns (e.g. timestep t of a [B, T*2H] layer output).  nullptr: A[z] is the origin.
   const void* a_origin;
   int64_t a_origin_cols;
+  // Tile-level hand-over from a producer LSTM GEMM still running (EpiLstm::sync_signal): rows [m0, m0+128) of A may be
+  // read once sync_wait[m0 >> sync_row_shift] >= sync_target.  nullptr: plain stream order.  Honoured by the 128x128
+  // tensor-core kernel only (the context projection).
+  const unsigned int* sync_wait;
+  unsigned int sync_target;
+  int sync_row_shift;
 };
 
 // ---------------------------------------------------------------- plain store (+bias, +tanh)

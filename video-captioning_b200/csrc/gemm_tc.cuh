@@ -244,6 +244,7 @@ struct TcArgs {
   unsigned int* sync_signal;
   const unsigned int* sync_wait;
   unsigned int sync_target;
+  int sync_row_shift;     // gemm_tc_kernel: counter index = m0 >> sync_row_shift
 };
 
 // ---------------------------------------------------------------- the kernel
@@ -300,12 +301,26 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs g) {
       tma_load_2d(smem_u32(smem + (size_t)kb * kStageBytes + kABytes), mapW, fb, kb * BK, n0);
     }
   }
-  pdl_wait();                 // everything above overlaps the tail of the previous kernel in the stream
+  // everything above overlaps the tail of the previous kernel in the stream; with a tile-level hand-over (sync_wait) the
+  // kernel does not wait for the previous grid as a whole but for the A rows of its own tile
+  const bool handover = EPI == EPI_STORE && g.sync_wait != nullptr;
+  if (!handover) pdl_wait();
   pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      if (handover) {
+        const unsigned int* flag = g.sync_wait + (m0 >> g.sync_row_shift);
+        uint32_t spin = 0;
+        while (ld_acquire_gpu_u32(flag) < g.sync_target) {
+          if (++spin > (1u << 26)) {
+            printf("vc::tc hand-over timeout (block %d,%d)\n", blockIdx.x, blockIdx.y);
+            __trap();
+          }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");     // order the acquire before the async-proxy loads
+      }
       if (EPI == EPI_LSTM) {
         // epilogue inputs first: they are resident long before the accumulator is
         const uint32_t ib = smem_u32(&in_bar);
@@ -1249,6 +1264,17 @@ inline unsigned int lstm_sync_arrivals(int M, int N) {
   if (N % 256 != 0 || tm * tn < num_sms()) return 0u;
   return use_mc(tm, tn) ? 2u * (unsigned)tn : (unsigned)tn;
 }
+// rows per hand-over counter of that LSTM GEMM, as a shift: 256-row pair tiles or 128-row tiles
+inline int lstm_sync_row_shift(int M, int N) {
+  const int tm = (M + BM - 1) / BM, tn = N / 256;
+  return use_mc(tm, tn) ? 8 : 7;
+}
+// The consumer side is implemented in the 128x128-tile kernel: true when a store-epilogue GEMM [M, N] takes that kernel
+// (see launch_gemm_tc: BN = 128 unless N >= 256 and there are at least #SMs 128x256 tiles)
+inline bool ctx_handover_ok(int M, int N) {
+  const int64_t tiles256 = (int64_t)((M + 127) / 128) * ((N + 255) / 256);
+  return !(N >= 256 && tiles256 >= num_sms());
+}
 // maps.W[1] <- the W operand with a 128-row box (each CTA of a pair stages half of the 256-row tile)
 inline int fill_w_half(TcMaps& mp, const GemmArgs& g, int esize) {
   return get_map(&mp.W[1], g.W[0], (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, 128u, esize);
@@ -1260,6 +1286,7 @@ inline int fill_ab(TcMaps& mp, TcArgs& ta, const GemmArgs& g, int64_t a_cols, in
   VC_CHECK(g.a_col0 % 8 == 0 && g.a_split % BK == 0 && g.a_skip % 8 == 0, "A column offsets must be multiples of 8/64");
   memset(&ta, 0, sizeof(ta));
   ta.M = g.M; ta.N = g.N; ta.K = g.K; ta.a_split = g.a_split; ta.a_skip = g.a_skip;
+  ta.sync_wait = g.sync_wait; ta.sync_target = g.sync_target; ta.sync_row_shift = g.sync_row_shift;
   for (int z = 0; z < 2; ++z) {
     const int zz = z < g.nz ? z : 0;
     int c0 = 0;
@@ -1303,6 +1330,7 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
   VC_TRY(fill_ab(mp, ta, g, a_cols, BN));
   ta.bias[0] = ta.bias[1] = e.bias[0];
   VC_TRY(get_map(&mp.io[0], e.C[0], (uint64_t)g.M, (uint64_t)g.N, (uint64_t)e.ldc, BM, sizeof(OutT)));
+  if (BN == 256) ta.sync_wait = nullptr;   // tile-level hand-over (GemmArgs::sync_wait) is a feature of the 128x128-tile kernel
   if (BN == 256) {
     // persistent, TMEM double-buffered: one CTA per SM loops over the tiles
     // (4 stages + staging + static smem would exceed the 227 KB limit)
