@@ -11,7 +11,7 @@ host = torch.randn(1024, 80, 4096).pin_memory()
 for label, setup in (("default", {}), ("c3", dict(host_chunk_fractions=(0.375, 0.75, 1.0))), ("c4", dict(host_chunk_fractions=(0.25, 0.5, 0.75, 1.0))),
                      ("c3b", dict(host_chunk_fractions=(0.5, 0.8, 1.0))), ("c4b", dict(host_chunk_fractions=(0.4, 0.7, 0.9, 1.0))),
                      ("c2b", dict(host_chunk_fractions=(0.75, 1.0))), ("default2", {}), ("nopack", dict(host_pack=False))):
-    m.host_pack_threads = 16; m.host_inflight = 3; m.host_chunk_fractions = (0.625, 1.0); m.host_pack = True
+    m.host_pack_threads = 16; m.host_inflight = 3; m.host_chunk_fractions = (0.625, 1.0); m.host_pack = True; m._ingest_trials = {}
     for k, v in setup.items(): setattr(m, k, v)
     for _ in range(2):
         o = m.generate(host, 1, 2, max_length=20, method="beam", beam_size=5); o["generated_tokens"].cpu()

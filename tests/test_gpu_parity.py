@@ -354,6 +354,7 @@ def test_host_packed_ingest_bf16(monkeypatch, piece, threads):
     V = cfg.model.vocab_size
     sd = synth.make_state_dict(cfg, V, "bahdanau", seed=71, logit_gain=4.0, end_token_id=END, end_bias=0.3)
     m = make_native_model(cfg, V, sd, "bahdanau", "bf16")
+    m.host_pack = True
     m.host_window_size = 14          # two windows (14 + 9 videos), three decode chunks each
     m.host_chunk_fractions = (0.3, 0.7, 1.0)
     m.host_piece_size = piece
@@ -367,9 +368,11 @@ def test_host_packed_ingest_bf16(monkeypatch, piece, threads):
             assert torch.equal(a["generated_tokens"], b["generated_tokens"])
             if method == "beam":
                 assert torch.equal(a["lengths"], b["lengths"]) and torch.equal(a["scores"], b["scores"])
-    m.host_pack = False          # plain fp32 transfer (tf32 feature projection): same tokens up to near-ties
-    c = m.generate(host, START, END, max_length=9, method="greedy")["generated_tokens"]
     a = m.generate(dev16, START, END, max_length=9, method="greedy")["generated_tokens"]
+    m.host_pack = False          # no host cores: every piece crosses as fp32 and is rounded on the device -- same result
+    assert torch.equal(m.generate(host, START, END, max_length=9, method="greedy")["generated_tokens"], a)
+    # device-resident fp32 features take the tf32 feature projection: same tokens up to near-ties
+    c = m.generate(host.cuda(), START, END, max_length=9, method="greedy")["generated_tokens"]
     n = min(a.shape[1], c.shape[1])
     assert (a[:, :n] == c[:, :n]).float().mean() > 0.9
 

@@ -86,7 +86,12 @@ class VideoCaptioningModel(nn.Module):
         self.host_chunk_size = 256         # videos per H2D chunk when the features live in host memory
         # bf16 mode: part of a host batch is rounded to bf16 on the host cores and crosses PCIe at half the size
         # (_generate_from_host_packed); VC_HOST_PACK=0 or host_pack=False keeps the plain fp32 transfer
-        self.host_pack = os.environ.get("VC_HOST_PACK", "1") != "0"
+        # "auto" (default): on when this rank has the node's host memory system mostly to itself.  Packing reads 1.31 MB and
+        # writes 0.66 MB per video next to the DMA reads; measured: 1 rank on a 16-core box 41-42k vs 35k captions/s with
+        # plain copies (wins); 4 ranks on a 32-core box 112k vs 137k for the node (loses); 2 ranks 72k (36k per GPU).
+        _hp = os.environ.get("VC_HOST_PACK", "auto")
+        _lw = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        self.host_pack = (_lw <= 2 and (os.cpu_count() or 1) // _lw >= 8) if _hp == "auto" else (_hp != "0")
         self.host_piece_size = int(os.environ.get("VC_HOST_PIECE", "64"))   # videos per transfer piece of the packed ingest
         self.host_inflight = 3             # piece copies queued ahead on the copy stream
         self.host_window_size = 1024       # videos staged on the device at a time (0.67 GB of bf16 at the MSVD shape)
@@ -152,8 +157,11 @@ class VideoCaptioningModel(nn.Module):
                                        beam_size=kwargs.get("beam_size", 5), length_penalty=kwargs.get("length_penalty", 1.0),
                                        temperature=kwargs.get("temperature", 1.0), diverse=kwargs.get("diverse_beams", False))
         if video_features.device.type == "cpu":
-            if self.precision == "bf16" and self.host_pack and video_features.dtype == torch.float32 and video_features.dim() == 3:
-                outs = self._generate_from_host_packed(h, video_features.contiguous(), video_mask, gen)
+            can_pack = self.precision == "bf16" and video_features.dtype == torch.float32 and video_features.dim() == 3
+            if can_pack:
+                # bf16 mode always goes through the piece pipeline (every feature rounded once to bf16, so the result does
+                # not depend on the route); host_pack only decides whether host cores take part
+                outs = self._generate_from_host_packed(h, video_features.contiguous(), video_mask, gen, pack=bool(self.host_pack))
             else:
                 outs = self._generate_from_host(h, video_features, video_mask, gen)
         else:
@@ -216,7 +224,7 @@ class VideoCaptioningModel(nn.Module):
             free[i % 2].record(compute)
         return outs
 
-    def _generate_from_host_packed(self, h, feats: torch.Tensor, mask, gen):
+    def _generate_from_host_packed(self, h, feats: torch.Tensor, mask, gen, pack: bool = True):
         """bf16-mode ingest of HOST fp32 features.  The PCIe link (54 GB/s, 1.3 MB per video) is the end-to-end
         bottleneck and bf16 mode rounds the features to bf16 anyway, so the batch is cut into pieces of
         ``host_piece_size`` videos that reach the device by one of two routes, whichever is free:
@@ -312,7 +320,7 @@ class VideoCaptioningModel(nn.Module):
             if w0 > 0:                        # later windows of the same call accumulate
                 stats["h2d_bytes"] = self.host_stats.get("h2d_bytes", 0)
             self.host_stats = stats
-            worker = threading.Thread(target=packer, daemon=True)
+            worker = threading.Thread(target=packer if pack else (lambda: None), daemon=True)
             worker.start()
             inflight = collections.deque()     # events of enqueued piece copies, oldest first
             n_raw = 0
