@@ -155,12 +155,8 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 inline bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VC_DISABLE_PDL");
-    v = (e != nullptr && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
+  const char* e = getenv("VC_DISABLE_PDL");          // read per launch: tests toggle it inside one process
+  return !(e != nullptr && e[0] == '1');
 }
 
 // cluster_x > 1: thread-block clusters of that many CTAs along x (grid.x must be a multiple of it)

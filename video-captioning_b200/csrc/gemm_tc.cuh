@@ -1250,12 +1250,9 @@ inline bool tma_ok(const void* p, int64_t ld, int esize) {
 // CTA-pair (cta_group::2) variant of the persistent kernel: even number of m-tiles and SMs, at least one pair-tile per pair.
 // VC_DISABLE_MC=1: single-CTA kernel everywhere (A/B).
 inline bool use_mc(int tm, int tn) {
-  static int en = -1;
-  if (en < 0) {
-    const char* e = getenv("VC_DISABLE_MC");
-    en = (e != nullptr && e[0] == '1') ? 0 : 1;
-  }
-  return en == 1 && tm % 2 == 0 && num_sms() % 2 == 0 && (int64_t)(tm / 2) * tn >= num_sms() / 2;
+  const char* e = getenv("VC_DISABLE_MC");          // read per call: tests toggle it inside one process
+  const bool en = !(e != nullptr && e[0] == '1');
+  return en && tm % 2 == 0 && num_sms() % 2 == 0 && (int64_t)(tm / 2) * tn >= num_sms() / 2;
 }
 // Arrivals per scheduled m-tile row and launch of the persistent LSTM GEMM's tile-level hand-over (EpiLstm::sync_*), or 0
 // when a decoder-form LSTM GEMM of this shape does not take the persistent path (then stacked layers use stream order).
