@@ -18,8 +18,10 @@
 // producers before they load h_t for step t+1.  The spin is safe because the launch is cooperative
 // (all CTAs co-resident) and bounded (trap instead of hang).
 //
-// Warp roles (352 threads): w0 = h_{t-1} TMA producer, w1 = TMEM alloc + MMA issuer, w2-5 = epilogue of
-// row-half 0, w6-9 = epilogue of row-half 1, w10 = input-projection TMA producer.
+// Warp roles (608 threads): w0 = h_{t-1} TMA producer, w1 = TMEM alloc + MMA issuer, w2-9 = epilogue of
+// row-half 0, w10-17 = epilogue of row-half 1 (two warps per TMEM lane quarter, each taking 16 of the tile's 32 hidden
+// units: the epilogue is on the step's critical path, so its latency matters more than its issue slots),
+// w18 = input-projection TMA producer.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -28,7 +30,8 @@
 namespace vc {
 namespace tc {
 
-constexpr int kPlThreads = 352;
+constexpr int kPlThreads = 608;
+constexpr int kPlEpiThreads = 256;  // epilogue threads per row-half
 constexpr int kPlStages = 3;
 constexpr int kPlBN = 128;          // gate columns per CTA = 32 hidden units
 
@@ -92,9 +95,9 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(smem_u32(&tmem_full[h]), 1);
-      mbar_init(smem_u32(&tmem_empty[h]), 128);
+      mbar_init(smem_u32(&tmem_empty[h]), kPlEpiThreads);
       mbar_init(smem_u32(&xp_full[h]), 1);
-      mbar_init(smem_u32(&xp_empty[h]), 128);
+      mbar_init(smem_u32(&xp_empty[h]), kPlEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 18) {
     if (lane == 0) {
       // ===== input-projection tile of (step, row-half) =====
       for (int t = 0; t < T; ++t) {
@@ -182,18 +185,19 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
         }
       }
     }
-  } else if (warp >= 2 && warp < 10) {
-    // ===== epilogue: fused LSTM cell, one row x 32 hidden units per thread =====
-    const int half = (warp - 2) >> 2;
+  } else if (warp >= 2 && warp < 18) {
+    // ===== epilogue: fused LSTM cell, one row x 16 hidden units per thread =====
+    const int half = (warp - 2) >> 3;
+    const int sub = ((warp - 2) >> 2) & 1;                // which 2 of the 4 32-column chunks (16 of the 32 hidden units)
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                          // row inside the half
-    const int et = (warp - 2 - half * 4) * 32 + lane;     // 0..127 inside the half
+    const int et = (warp - 2 - half * 8) * 32 + lane;     // 0..255 inside the half
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
     const uint32_t hbox = smem_u32(h_s + (size_t)half * (128 * 64));
     const uint32_t xs = smem_u32(xp_s);
-    float c[32];
+    float c[16];
 #pragma unroll
-    for (int u = 0; u < 32; ++u) c[u] = 0.f;
+    for (int u = 0; u < 16; ++u) c[u] = 0.f;
     for (int t = 0; t < T; ++t) {
       const int tt = (z == 0) ? t : (T - 1 - t);
       mbar_wait(smem_u32(&xp_full[half]), (uint32_t)(t & 1));
@@ -202,7 +206,8 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
         tc_fence_after();
       }
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
+      for (int cj = 0; cj < 2; ++cj) {
+        const int ci = 2 * sub + cj;
         uint32_t v[32];
         if (t > 0) {
           tmem_ld32(taddr + (uint32_t)(ci * 32), v);
@@ -232,8 +237,8 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
           const float fg = sigmoid_<false>(gte[4 * u + 1]);
           const float gg = tanh_<false>(gte[4 * u + 2]);
           const float og = sigmoid_<false>(gte[4 * u + 3]);
-          const float cn = fmaf(fg, c[ci * 8 + u], ig * gg);
-          c[ci * 8 + u] = cn;
+          const float cn = fmaf(fg, c[cj * 8 + u], ig * gg);
+          c[cj * 8 + u] = cn;
           hn[u] = og * tanh_<false>(cn);
         }
         sts128(swz64(hbox, r, ci), pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]),
@@ -245,13 +250,13 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
       }
       mbar_arrive(smem_u32(&xp_empty[half]));             // input-projection tile consumed
       fence_proxy_async_smem();
-      asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+      asm volatile("bar.sync %0, 256;" ::"r"(2 + half) : "memory");
       if (et == 0) {
         tma_store_2d(&maps.out_st, hbox, tt * 2 * H + z * H + n0 / 4, m0 + half * 128);
         tma_store_commit();
         tma_store_wait_read();                            // staging box may be rewritten
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+      asm volatile("bar.sync %0, 256;" ::"r"(2 + half) : "memory");
       if (et == 0) {
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // h_t slice is in global memory
         asm volatile("fence.proxy.async;" ::: "memory");
