@@ -7,6 +7,9 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -46,6 +49,68 @@ __attribute__((target("avx512f,avx512bw"))) void pack_avx512(const float* s, uin
   for (; i < n; ++i) d[i] = pack_one(s[i]);
 }
 
+// Persistent worker pool: a piece of the ingest is ~1.5 ms of work, creating 16 threads per call would cost a fifth of it.
+// One job at a time (callers are serialised by `submit_mu`); workers sleep on a condition variable between jobs.
+class Pool {
+ public:
+  static Pool& get() {
+    static Pool* p = new Pool();   // leaked on purpose: worker threads must not be joined during static destruction
+    return *p;
+  }
+  // run fn(t) for t in [0, parts) on the workers (+ the caller for part 0); returns when all parts are done
+  void run(int parts, const std::function<void(int)>& fn) {
+    std::lock_guard<std::mutex> submit(submit_mu_);
+    if (parts <= 1) { fn(0); return; }
+    grow(parts - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      parts_ = parts;
+      next_ = 1;
+      pending_ = parts - 1;
+      ++gen_;
+    }
+    cv_.notify_all();
+    fn(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void grow(int n) {
+    while ((int)workers_.size() < n) {
+      workers_.emplace_back([this] { loop(); });
+      workers_.back().detach();
+    }
+  }
+  void loop() {
+    unsigned long seen = 0;
+    for (;;) {
+      const std::function<void(int)>* fn = nullptr;
+      int part = -1;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen && fn_ != nullptr && next_ < parts_; });
+        part = next_++;
+        if (next_ >= parts_) seen = gen_;     // the last part of this job: wait for the next generation afterwards
+        fn = fn_;
+      }
+      (*fn)(part);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  std::mutex submit_mu_, mu_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> workers_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int parts_ = 0, next_ = 0, pending_ = 0;
+  unsigned long gen_ = 0;
+};
+
 }  // namespace
 
 // dst[i] = bf16(src[i]) (round to nearest even), i < n, on `threads` host threads.  Returns 0.
@@ -63,13 +128,10 @@ extern "C" int vc_host_pack_bf16(const float* src, uint16_t* dst, size_t n, int3
     return 0;
   }
   const size_t per = ((n + threads - 1) / threads + 63) & ~(size_t)63;
-  std::vector<std::thread> pool;
-  pool.reserve(threads);
-  for (int t = 0; t < threads; ++t) {
+  const int parts = (int)((n + per - 1) / per);
+  Pool::get().run(parts, [&](int t) {
     const size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
-    if (lo >= n) break;
-    pool.emplace_back(run, lo, hi);
-  }
-  for (auto& th : pool) th.join();
+    run(lo, hi);
+  });
   return 0;
 }

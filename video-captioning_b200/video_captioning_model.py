@@ -95,7 +95,7 @@ class VideoCaptioningModel(nn.Module):
         self.host_piece_size = int(os.environ.get("VC_HOST_PIECE", "64"))   # videos per transfer piece of the packed ingest
         self.host_inflight = 3             # piece copies queued ahead on the copy stream
         self.host_window_size = 1024       # videos staged on the device at a time (0.67 GB of bf16 at the MSVD shape)
-        self.host_chunk_fractions = tuple(float(x) for x in os.environ.get("VC_HOST_CHUNKS", "0.625,1.0").split(","))
+        self.host_chunk_fractions = tuple(float(x) for x in os.environ.get("VC_HOST_CHUNKS", "0.5,0.8,1.0").split(","))
         self.host_pack_threads = int(os.environ.get("VC_HOST_PACK_THREADS", "0")) or max(
             1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
         self._packed = None
