@@ -414,7 +414,8 @@ def test_cuda_graph_replay_equals_plain_launches(precision):
 def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
     """The benchmark configuration (1024 MSVD-shape videos, beam 5, bf16) is the only size at which the persistent CTA-pair
     GEMMs (tcgen05 cta_group::2), the tile-level hand-over between the stacked decoder LSTM GEMMs / the context
-    projection, programmatic dependent launch and the shared pruning threshold of the vocabulary GEMM are all active.
+    projection, programmatic dependent launch, the early query projection on a second stream and the shared pruning
+    threshold of the vocabulary GEMM are all active.
     Switching each of them off must not change a single token, length or score: they reorder launches and move the
     same arithmetic between kernels, but every accumulation runs in the same order.  (The arithmetic itself is pinned
     against the oracle at smaller sizes above.)"""
@@ -427,7 +428,7 @@ def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
 
     def run(**env):
         for k in ("VC_DISABLE_LAYER_SYNC", "VC_DISABLE_CTX_HANDOVER", "VC_DISABLE_MC", "VC_DISABLE_PDL", "VC_DISABLE_SHARED_THR",
-                  "VC_CUDA_GRAPHS"):
+                  "VC_CUDA_GRAPHS", "VC_DISABLE_EARLY_Q"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -449,7 +450,7 @@ def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
     same = (small["generated_tokens"].cpu() == ref["generated_tokens"][:48, :L]).all(dim=1).float().mean().item()
     assert same >= 0.9, same          # different attention kernels (v4 / v5): near-ties may flip
     for env in (dict(VC_DISABLE_LAYER_SYNC="1"), dict(VC_DISABLE_CTX_HANDOVER="1"), dict(VC_DISABLE_MC="1"),
-                dict(VC_DISABLE_SHARED_THR="1"), dict(VC_CUDA_GRAPHS="0"), dict(VC_DISABLE_PDL="1")):
+                dict(VC_DISABLE_SHARED_THR="1"), dict(VC_CUDA_GRAPHS="0"), dict(VC_DISABLE_PDL="1"), dict(VC_DISABLE_EARLY_Q="1")):
         got = run(**env)
         for k in ref:
             assert torch.equal(got[k], ref[k]), (env, k)

@@ -373,6 +373,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_step_kernel(const AttnArgs<
 struct AttnAddArgs {
   const __half* keys;    // [B, T, D] fp16 projected keys (attention.py:52 / :140)
   const __half* q;       // [R, D] fp16 projected queries incl. bias (attention.py:53 / :138)
+  const int* q_rows;     // nullptr, or [R]: row r's query is q[q_rows[r]] -- the projection ran on the rows BEFORE the beam
+                         // reorder (overlapped with the selection), so the reorder is applied here as an indirection
   const __half* v;       // [D] fp16 score vector (attention.py:28 / :99)
   float v_bias;
   const bf16* values;    // [B, T, H] enc_out
@@ -438,7 +440,10 @@ __global__ void __launch_bounds__(kAddThreads, 7) attn_additive_kernel(const Att
     uint4 qreg[K];
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int k = 0; k < K; ++k) qreg[k] = live ? ldg128(a.q + ((int64_t)b * K + k) * D + d0) : zero4;
+    for (int k = 0; k < K; ++k) {
+      const int64_t qr = a.q_rows ? (int64_t)a.q_rows[b * K + k] : (int64_t)b * K + k;
+      qreg[k] = live ? ld128(a.q + qr * D + d0) : zero4;
+    }
     const uint4 vreg = live ? ldg128(a.v + d0) : zero4;           // v = 0: dead lanes contribute nothing
     const __half* kp = a.keys + (int64_t)b * T * D + d0;
     float* prow = part + dh * K * Tp;
@@ -652,8 +657,11 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) attn_additive_mma_kernel(co
   for (int i = tid; i < D / 8; i += kMmaThreads) reinterpret_cast<uint4*>(v_s)[i] = ldg128(a.v + (int64_t)i * 8);
   pdl_wait();
   pdl_launch_dependents();
-  for (int i = tid; i < K * D / 8; i += kMmaThreads)
-    reinterpret_cast<uint4*>(q_s)[i] = ld128(a.q + (int64_t)b * K * D + (int64_t)i * 8);
+  for (int i = tid; i < K * D / 8; i += kMmaThreads) {
+    const int k = (i * 8) / D, off = i * 8 - k * D;
+    const int64_t qr = a.q_rows ? (int64_t)a.q_rows[b * K + k] : (int64_t)b * K + k;
+    reinterpret_cast<uint4*>(q_s)[i] = ld128(a.q + qr * D + off);
+  }
   __syncthreads();
 
   // ---- scores: warp w owns feature blocks fb = w, w+4, ... (32 features each)
@@ -916,12 +924,12 @@ __global__ void __launch_bounds__(32 * (4 * NG + 4 * NCG + 1), 1) attn_additive_
     __half* q_w = q_s + (size_t)warp * 2 * K * 128;
     // this warp's query columns (feature blocks sw, sw+4, ...) of video b -> private buffer
     auto load_q = [&](int b, int buf) {
-      const __half* src = a.q + (int64_t)b * K * D;
       const uint32_t dst = (uint32_t)__cvta_generic_to_shared(q_w + (size_t)buf * K * 128);
       for (int i = lane; i < K * 16; i += 32) {  // i = (k*4 + j)*4 + c: 16-byte chunk c of block j of beam k
         const int c = i & 3, j = (i >> 2) & 3, k = i >> 4;
         const int fb = sw + 4 * j;
-        if (fb < nfb) cp_async16(dst + (uint32_t)i * 16u, src + (int64_t)k * D + fb * 32 + c * 8);
+        const int64_t qr = a.q_rows ? (int64_t)a.q_rows[b * K + k] : (int64_t)b * K + k;
+        if (fb < nfb) cp_async16(dst + (uint32_t)i * 16u, a.q + qr * D + fb * 32 + c * 8);
       }
       cp_async_commit();
     };

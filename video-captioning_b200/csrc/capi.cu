@@ -117,6 +117,9 @@ struct vc_model {
   bool disable_tf32_proj = false;         // VC_DISABLE_TF32_PROJ=1: convert the features to bf16 first (A/B testing)
   int dbg_vocab = 0;                      // VC_DEBUG_VOCAB: timing experiments (gemm_tc.cuh VocabStats::dbg), results invalid
   bool disable_fused_reorder = true;      // VC_FUSED_REORDER=1: the fused selection kernel also does the reorder/embedding gather (measured slower than the separate PDL launch: 54 vs 33 + 20 us per step)
+  bool disable_early_q = false;           // VC_DISABLE_EARLY_Q=1: query projection in place, after the reorder (A/B testing)
+  cudaStream_t aux_stream = nullptr;      // second stream of the decode loop (early query projection)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool disable_ctx_handover = false;      // VC_DISABLE_CTX_HANDOVER=1: the context projection waits for the last LSTM GEMM as a whole (A/B testing)
   bool disable_layer_sync = false;        // VC_DISABLE_LAYER_SYNC=1: stacked decoder LSTM GEMMs in plain stream order (A/B testing)
   bool disable_shared_thr = false;        // VC_DISABLE_SHARED_THR=1: per-CTA pruning thresholds only in the vocab GEMM (A/B testing)
@@ -141,6 +144,9 @@ struct vc_model {
   void* Wv = nullptr; float* bv = nullptr;
 
   ~vc_model() {
+    if (aux_stream) cudaStreamDestroy(aux_stream);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     for (void* p : owned) cudaFree(p);
     for (auto& kv : raw) cudaFree(kv.second.first);
   }
@@ -604,7 +610,8 @@ int run_precompute(vc_model* m, WS<ActT>& w, int B, int T, cudaStream_t s) {
 // hq: [R, *] previous top-layer hidden state (row stride hq_ld, `hq_cols` addressable columns from hq).
 template <class ActT>
 int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64_t hq_cols, const float* mask, int B, int T,
-                  int K, ActT* ctx, int64_t ctx_ld, float* attn_out, int64_t attn_ld, cudaStream_t s) {
+                  int K, ActT* ctx, int64_t ctx_ld, float* attn_out, int64_t attn_ld, cudaStream_t s, bool q_ready = false,
+                  const int* q_rows = nullptr) {
   constexpr bool P = std::is_same<ActT, float>::value;
   const vc_model_desc_t& d = m->d;
   const int H = d.hidden_dim, A = d.attn_dim, R = B * K;
@@ -621,11 +628,12 @@ int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64
         if (!m->disable_attn_v3 && (use_ws || use_mma || attn_additive_fast_ok(K, A, H))) {
           // queries leave the projection GEMM as fp16 and are consumed from registers by the v3 kernel
           __half* q16 = reinterpret_cast<__half*>(w.Q);
-          {
+          if (!q_ready) {     // (q_ready: run_decode projected the queries early, on the rows before the reorder: q_rows)
             VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
             VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, A, H), hq_cols, estore<__half, false, P>(q16, A, m->bq), s)));
           }
           AttnAddArgs aa;
+          aa.q_rows = q_rows;
           aa.keys = reinterpret_cast<const __half*>(w.keys); aa.q = q16; aa.v = m->vvec_h; aa.v_bias = m->vbias;
           aa.values = w.enc_act; aa.mask = mask; aa.ctx = ctx; aa.ctx_ld = ctx_ld; aa.attn_out = attn_out; aa.attn_ld = attn_ld;
           aa.B = B; aa.T = T; aa.D = A; aa.H = H;
@@ -682,6 +690,19 @@ int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64
   return VC_ERR_INVALID;
 }
 
+// true when run_attention takes the additive fast path with fp16 queries in w.Q (the path whose query projection
+// run_decode may issue early)
+template <class ActT>
+bool additive_fast_path(const vc_model* m, int B, int T, int K, int64_t ctx_ld, bool weights) {
+  if (std::is_same<ActT, float>::value) return false;
+  const vc_model_desc_t& d = m->d;
+  if (d.attention != VC_ATTN_BAHDANAU && d.attention != VC_ATTN_LUONG_CONCAT) return false;
+  const int H = d.hidden_dim, A = d.attn_dim;
+  const bool use_mma = m->attn_variant >= 4 && attn_additive_mma_ok(K, A, H, T) && ctx_ld % 8 == 0;
+  const bool use_ws = m->attn_variant >= 5 && attn_additive_ws_ok(B, K, A, H, T, weights) && ctx_ld % 8 == 0;
+  return !m->disable_attn_v3 && (use_ws || use_mma || attn_additive_fast_ok(K, A, H));
+}
+
 // ---------------------------------------------------------------- decode loop
 enum DecodeMode { DM_GREEDY = 0, DM_BEAM = 1, DM_TEACHER = 2 };
 
@@ -730,10 +751,28 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
   const int64_t hq_ld = st.x_ld[L - 1];
   const int64_t hq_cols = H;   // columns addressable from hq within its row
 
+  // Early query projection (additive attention, bf16): the queries of step t+1 only need this step's top-layer h, so their
+  // projection is issued right after the LSTM layers on a second stream and runs beside the context / vocabulary
+  // projections and the (latency-bound) selection; the beam reorder is applied by the attention kernel as a row
+  // indirection (parent).  Fork / join through events, so the pattern also records into a CUDA graph.
+  bool early_q = false;
+  if constexpr (!P) {
+    early_q = !m->disable_early_q && S > 1 && additive_fast_path<ActT>(m, B, T, K, ZW, attn_out != nullptr);
+    if (early_q && m->aux_stream == nullptr) {
+      VC_CUDA(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
+      VC_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+      VC_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    }
+  }
+  const int* q_rows = nullptr;     // rows of w.Q for the next attention step (the previous selection's parents)
+  bool q_pending = false;
+
   for (int step = 0; step < S; ++step) {
     // attention on the previous step's top-layer h (decoder.py:135-138) -> ctx segment of Z
     float* aw = attn_out ? attn_out + (size_t)step * T : nullptr;
-    VC_TRY((run_attention<ActT>(m, w, hq, hq_ld, hq_cols, mask, B, T, K, w.Z + E, ZW, aw, (int64_t)S * T, s)));
+    if (q_pending) VC_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));
+    VC_TRY((run_attention<ActT>(m, w, hq, hq_ld, hq_cols, mask, B, T, K, w.Z + E, ZW, aw, (int64_t)S * T, s, q_pending, q_rows)));
+    q_pending = false;
     // L-layer LSTM, one step (:152): gates = [x | h_prev] . [W_ih | W_hh]^T + (b_ih + b_hh), fused cell
     for (int l = 0; l < L; ++l) {
       const int in = (l == 0) ? (E + H) : H;
@@ -764,6 +803,23 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       }
       VC_SCOPE(VC_CLS_DEC_LSTM);
       VC_TRY((gemm<ActT>(g, lda, e, s)));
+    }
+    if constexpr (!P) {
+      if (early_q && step + 1 < S) {
+        // queries of step+1 from this step's new top-layer h (rows before the reorder), on the second stream
+        VC_CUDA(cudaEventRecord(m->ev_fork, s));
+        VC_CUDA(cudaStreamWaitEvent(m->aux_stream, m->ev_fork, 0));
+        {
+          cudaStream_t s_main = s;
+          cudaStream_t s = m->aux_stream;     // (LaunchScope below brackets the launch on the stream it runs on)
+          (void)s_main;
+          VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
+          VC_TRY((gemm<ActT>(gargs(w.Z + (E + 2 * H), ZW, m->Wq, H, R, d.attn_dim, H), (int64_t)H,
+                             estore<__half, false, P>(reinterpret_cast<__half*>(w.Q), d.attn_dim, m->bq), s)));
+        }
+        VC_CUDA(cudaEventRecord(m->ev_join, m->aux_stream));
+        q_pending = true;
+      }
     }
     // tanh(context_projection([h_top ; ctx ; emb])) (:157-165), operands read in place from Z
     {
@@ -833,6 +889,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       set_tokens_kernel<<<(R + 127) / 128, 128, 0, s>>>(w.cur_tok, teacher_tokens, S, step + 1, R);
     }
     VC_CUDA(cudaGetLastError());
+    q_rows = parent;     // the next step's early-projected queries are indexed by this step's parents (nullptr: identity)
     if (step + 1 < S && !reorder_done) {
       VC_SCOPE(VC_CLS_REORDER_EMBED);
       VC_CUDA(launch_pdl(reorder_embed_kernel<ActT>, dim3(R), dim3(128), 0, s, st, parent, (const int*)w.cur_tok, V));
@@ -946,6 +1003,8 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   m->dbg_vocab = env != nullptr ? atoi(env) : 0;
   env = getenv("VC_FUSED_REORDER");
   m->disable_fused_reorder = !(env != nullptr && env[0] == '1');
+  env = getenv("VC_DISABLE_EARLY_Q");
+  m->disable_early_q = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_CTX_HANDOVER");
   m->disable_ctx_handover = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_LAYER_SYNC");
