@@ -117,6 +117,7 @@ struct vc_model {
   bool disable_tf32_proj = false;         // VC_DISABLE_TF32_PROJ=1: convert the features to bf16 first (A/B testing)
   int dbg_vocab = 0;                      // VC_DEBUG_VOCAB: timing experiments (gemm_tc.cuh VocabStats::dbg), results invalid
   bool disable_fused_reorder = true;      // VC_FUSED_REORDER=1: the fused selection kernel also does the reorder/embedding gather (measured slower than the separate PDL launch: 54 vs 33 + 20 us per step)
+  bool early_attn = false;                // VC_EARLY_ATTN=1: the next step's attention also runs on the second stream, before the reorder
   bool disable_early_q = false;           // VC_DISABLE_EARLY_Q=1: query projection in place, after the reorder (A/B testing)
   cudaStream_t aux_stream = nullptr;      // second stream of the decode loop (early query projection)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -766,13 +767,20 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
   }
   const int* q_rows = nullptr;     // rows of w.Q for the next attention step (the previous selection's parents)
   bool q_pending = false;
+  // Early attention (VC_EARLY_ATTN=1): the whole attention step of t+1 -- it only depends on (video, query) -- also runs on
+  // the second stream, on the rows before the reorder, into w.ctx_pre; the reorder kernel gathers the contexts by parent.
+  const bool early_attn = early_q && m->early_attn && m->disable_fused_reorder;
+  if (early_attn) { st.ctx_src = w.ctx_pre; st.ctx_dst = w.Z + E; st.ctx_ld = ZW; }
+  bool attn_pending = false;
 
   for (int step = 0; step < S; ++step) {
     // attention on the previous step's top-layer h (decoder.py:135-138) -> ctx segment of Z
     float* aw = attn_out ? attn_out + (size_t)step * T : nullptr;
-    if (q_pending) VC_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));
-    VC_TRY((run_attention<ActT>(m, w, hq, hq_ld, hq_cols, mask, B, T, K, w.Z + E, ZW, aw, (int64_t)S * T, s, q_pending, q_rows)));
-    q_pending = false;
+    if (!(early_attn && step > 0)) {
+      if (q_pending) VC_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));
+      VC_TRY((run_attention<ActT>(m, w, hq, hq_ld, hq_cols, mask, B, T, K, w.Z + E, ZW, aw, (int64_t)S * T, s, q_pending, q_rows)));
+      q_pending = false;
+    }
     // L-layer LSTM, one step (:152): gates = [x | h_prev] . [W_ih | W_hh]^T + (b_ih + b_hh), fused cell
     for (int l = 0; l < L; ++l) {
       const int in = (l == 0) ? (E + H) : H;
@@ -817,8 +825,15 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
           VC_TRY((gemm<ActT>(gargs(w.Z + (E + 2 * H), ZW, m->Wq, H, R, d.attn_dim, H), (int64_t)H,
                              estore<__half, false, P>(reinterpret_cast<__half*>(w.Q), d.attn_dim, m->bq), s)));
         }
+        if (early_attn) {
+          float* aw_next = attn_out ? attn_out + (size_t)(step + 1) * T : nullptr;
+          VC_TRY((run_attention<ActT>(m, w, hq, hq_ld, hq_cols, mask, B, T, K, w.ctx_pre, H, aw_next, (int64_t)S * T, m->aux_stream,
+                                      /*q_ready=*/true, /*q_rows=*/nullptr)));
+          attn_pending = true;
+        } else {
+          q_pending = true;
+        }
         VC_CUDA(cudaEventRecord(m->ev_join, m->aux_stream));
-        q_pending = true;
       }
     }
     // tanh(context_projection([h_top ; ctx ; emb])) (:157-165), operands read in place from Z
@@ -890,6 +905,10 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
     }
     VC_CUDA(cudaGetLastError());
     q_rows = parent;     // the next step's early-projected queries are indexed by this step's parents (nullptr: identity)
+    if (attn_pending) {    // the reorder below gathers the early attention's contexts
+      VC_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));
+      attn_pending = false;
+    }
     if (step + 1 < S && !reorder_done) {
       VC_SCOPE(VC_CLS_REORDER_EMBED);
       VC_CUDA(launch_pdl(reorder_embed_kernel<ActT>, dim3(R), dim3(128), 0, s, st, parent, (const int*)w.cur_tok, V));
@@ -1003,6 +1022,8 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   m->dbg_vocab = env != nullptr ? atoi(env) : 0;
   env = getenv("VC_FUSED_REORDER");
   m->disable_fused_reorder = !(env != nullptr && env[0] == '1');
+  env = getenv("VC_EARLY_ATTN");
+  m->early_attn = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_EARLY_Q");
   m->disable_early_q = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_CTX_HANDOVER");

@@ -25,6 +25,11 @@ struct DecState {
   ActT* emb_dst;         // embedding destination inside layer 0's A buffer (row stride emb_ld)
   int64_t emb_ld;
   const ActT* emb_table; // [V,E]
+  // attention contexts computed ahead of the selection on the rows BEFORE the reorder (capi.cu: early attention):
+  // row r takes ctx_src[parent[r]].  nullptr: the attention step writes the context segment itself.
+  const ActT* ctx_src;   // [R,H]
+  ActT* ctx_dst;         // context segment inside layer 0's A buffer (row stride ctx_ld)
+  int64_t ctx_ld;
 };
 
 // ---------------------------------------------------------------- init (step -1)
@@ -661,6 +666,15 @@ __global__ void __launch_bounds__(128) reorder_embed_kernel(DecState<ActT> st, c
       load4(hs + u, hv);
       store4(hd + u, hv);
       *reinterpret_cast<float4*>(cd + u) = *reinterpret_cast<const float4*>(cs + u);
+    }
+  }
+  if (st.ctx_src != nullptr) {
+    const ActT* xs = st.ctx_src + (int64_t)p * st.H;
+    ActT* xd = st.ctx_dst + (int64_t)r * st.ctx_ld;
+    for (int u = threadIdx.x * 4; u < st.H; u += blockDim.x * 4) {
+      float xv[4];
+      load4(xs + u, xv);
+      store4(xd + u, xv);
     }
   }
   int tok = __ldcg(cur_tok + r);
