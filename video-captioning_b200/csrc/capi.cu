@@ -760,7 +760,10 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
   if constexpr (!P) {
     early_q = !m->disable_early_q && S > 1 && additive_fast_path<ActT>(m, B, T, K, ZW, attn_out != nullptr);
     if (early_q && m->aux_stream == nullptr) {
-      VC_CUDA(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
+      int prio_lo = 0, prio_hi = 0;
+      VC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      // lowest priority: work on this stream fills what the main stream's kernels leave free
+      VC_CUDA(cudaStreamCreateWithPriority(&m->aux_stream, cudaStreamNonBlocking, prio_lo));
       VC_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
       VC_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     }
