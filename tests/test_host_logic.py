@@ -139,3 +139,42 @@ def test_host_pack_bf16_matches_round_to_nearest_even():
             a, b = dst.view(torch.int16), ref[off:].view(torch.int16)
             nan = torch.isnan(src)
             assert torch.equal(a[~nan], b[~nan]) and torch.isnan(dst[nan]).all()
+
+
+def test_packed_ingest_chunk_schedule():
+    """Decode chunks of the packed host ingest: contiguous cover of the window, piece-aligned cuts, last chunk smallest of
+    the defaults (its decode is the part of a step no transfer overlaps)."""
+    import video_captioning_b200 as vc
+    from oracle import synth
+    m = vc.VideoCaptioningModel(synth.make_config("tiny"), 1000, precision="bf16")
+    for (w0, w1, piece) in ((0, 1024, 64), (0, 23, 2), (14, 23, 2), (0, 5, 8), (100, 1124, 64), (0, 1000, 64)):
+        ch = m._packed_chunks(w0, w1, piece)
+        assert ch[0][0] == w0 and ch[-1][1] == w1
+        for (a, b), (c, d) in zip(ch, ch[1:]):
+            assert b == c and a < b
+        for a, b in ch[:-1]:
+            assert (b - w0) % piece == 0
+    ch = m._packed_chunks(0, 1024, 64)
+    assert [b - a for a, b in ch] == [512, 320, 192]
+    m.host_chunk_fractions = (1.0,)
+    assert m._packed_chunks(0, 1024, 64) == [(0, 1024)]
+
+
+def test_host_pack_auto_depends_on_ranks_per_node(monkeypatch):
+    """Host-side packing shares the node's cores and memory bandwidth: on for at most two ranks per node (measured),
+    always overridable."""
+    import video_captioning_b200 as vc
+    from oracle import synth
+    cfg = synth.make_config("tiny")
+    monkeypatch.delenv("VC_HOST_PACK", raising=False)
+    monkeypatch.setattr("os.cpu_count", lambda: 32)
+    for lw, want in (("1", True), ("2", True), ("4", False), ("8", False)):
+        monkeypatch.setenv("LOCAL_WORLD_SIZE", lw)
+        assert vc.VideoCaptioningModel(cfg, 1000, precision="bf16").host_pack is want
+    monkeypatch.setattr("os.cpu_count", lambda: 4)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert vc.VideoCaptioningModel(cfg, 1000, precision="bf16").host_pack is False      # too few cores to be worth it
+    monkeypatch.setenv("VC_HOST_PACK", "1")
+    assert vc.VideoCaptioningModel(cfg, 1000, precision="bf16").host_pack is True
+    monkeypatch.setenv("VC_HOST_PACK", "0")
+    assert vc.VideoCaptioningModel(cfg, 1000, precision="bf16").host_pack is False
