@@ -456,6 +456,36 @@ def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
             assert torch.equal(got[k], ref[k]), (env, k)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1000, 1030])
+def test_ragged_full_size_batches(monkeypatch, B):
+    """Batches that do not fill the last tiles of the persistent kernels: B=1000 (5000 rows: 40 m-tiles, CTA pairs, last tile
+    ragged) and B=1030 (5150 rows: 41 m-tiles, odd -> single-CTA persistent kernels with the tile hand-over).  The result
+    must not change when the scheduling features are switched off, and rows must agree with a small-batch call."""
+    from oracle import synth
+    cfg = synth.make_config("msvd")
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, "bahdanau", seed=0, logit_gain=8.0, end_token_id=END, end_bias=0.45)
+    g = torch.Generator(device="cuda").manual_seed(B)
+    x = torch.randn(B, 80, 4096, generator=g, device="cuda")
+    outs = []
+    for env in ({}, dict(VC_DISABLE_LAYER_SYNC="1", VC_DISABLE_MC="1", VC_DISABLE_PDL="1", VC_DISABLE_EARLY_Q="1", VC_CUDA_GRAPHS="0")):
+        for k in ("VC_DISABLE_LAYER_SYNC", "VC_DISABLE_MC", "VC_DISABLE_PDL", "VC_DISABLE_EARLY_Q", "VC_CUDA_GRAPHS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = make_native_model(cfg, V, sd, "bahdanau", "bf16")
+        o = m.generate(x, START, END, max_length=6, method="beam", beam_size=5)
+        outs.append({k: v.cpu() for k, v in o.items()})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    tail = make_native_model(cfg, V, sd, "bahdanau", "bf16").generate(x[B - 40:].clone(), START, END, max_length=6, method="beam",
+                                                                     beam_size=5)["generated_tokens"].cpu()
+    L = tail.shape[1]
+    same = (tail == outs[0]["generated_tokens"][B - 40:, :L]).all(dim=1).float().mean().item()
+    assert same >= 0.9, same
+
+
 # ------------------------------------------------------------------ fused selection (vocab-GEMM statistics) == streaming selection
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,V,B,K", [("tiny", 1000, 9, 5), ("tiny", 2500, 5, 3), ("small", 10000, 6, 5),
