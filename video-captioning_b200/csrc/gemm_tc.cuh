@@ -18,6 +18,19 @@
 //
 // Descriptor bit layouts follow the PTX ISA tcgen05 "shared memory descriptor" / "instruction
 // descriptor" tables (cross-checked against cute/arch/mma_sm100_desc.hpp in the image).
+//
+// Kernels in this file:
+//   gemm_tc_kernel             one 128 x BN tile per CTA (small GEMMs: query / context projections; masked encoder steps);
+//                              the 128x128 store variant can take its A rows over tile row by tile row from a producer
+//                              LSTM GEMM that is still running (GemmArgs::sync_wait)
+//   gemm_tc_persistent_kernel  one CTA per SM loops over 128 x 256 tiles, two TMEM accumulators (epilogue of tile i overlaps
+//                              the main loop of tile i+1); store / fused-LSTM / vocabulary-statistics epilogues; kind::f16 or
+//                              kind::tf32 operands; MC = CTA pairs (clusters of 2, tcgen05 cta_group::2, 256 x 256 pair tiles,
+//                              4-5 stage ring of 32 KB stages); stacked LSTM GEMMs hand their h rows over per tile row
+//                              (EpiLstm::sync_signal / sync_wait) instead of kernel by kernel
+//   gemm_tc_direct_kernel      generic functor epilogue (packed-sequence masking, unaligned outputs)
+// All are launched with the programmatic-dependent-launch attribute (common.cuh): the prologue and the first weight loads
+// overlap the previous kernel's tail.
 #pragma once
 #include <cuda.h>
 #include <cudaTypedefs.h>
