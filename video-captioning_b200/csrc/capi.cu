@@ -117,6 +117,7 @@ struct vc_model {
   bool disable_tf32_proj = false;         // VC_DISABLE_TF32_PROJ=1: convert the features to bf16 first (A/B testing)
   int dbg_vocab = 0;                      // VC_DEBUG_VOCAB: timing experiments (gemm_tc.cuh VocabStats::dbg), results invalid
   bool disable_fused_reorder = true;      // VC_FUSED_REORDER=1: the fused selection kernel also does the reorder/embedding gather (measured slower than the separate PDL launch: 54 vs 33 + 20 us per step)
+  bool feat_cvt = false;                  // VC_FEAT_CVT=1: feature projection with fp32 -> bf16 converting producer warps instead of tf32 operands
   bool early_attn = false;                // VC_EARLY_ATTN=1: the next step's attention also runs on the second stream, before the reorder
   bool disable_early_q = false;           // VC_DISABLE_EARLY_Q=1: query projection in place, after the reorder (A/B testing)
   cudaStream_t aux_stream = nullptr;      // second stream of the decode loop (early query projection)
@@ -461,6 +462,12 @@ int run_encoder(vc_model* m, WS<ActT>& w, const void* feats_any, int feats_dtype
     proj_done = true;
   }
   if constexpr (!P) {
+    if (!proj_done && m->feat_cvt && H >= 256 && F % 64 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0) {
+      // bf16 mode, fp32 features: the GEMM's producer warps round A to bf16 on the way into shared memory (bf16 MMA rate)
+      VC_SCOPE(VC_CLS_ENC_FEATURE_PROJ);
+      VC_TRY(tc::launch_gemm_tc_cvt(feats, F, m->Wp, F, BT, H, F, estore<bf16, false, false>(w.proj, H, m->bp), s));
+      proj_done = true;
+    }
     if (proj_done) {
     } else
     // bf16 mode: the tensor cores read the fp32 features (and the fp32 weight copy) as tf32 -- no conversion pass
@@ -1025,6 +1032,8 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   m->dbg_vocab = env != nullptr ? atoi(env) : 0;
   env = getenv("VC_FUSED_REORDER");
   m->disable_fused_reorder = !(env != nullptr && env[0] == '1');
+  env = getenv("VC_FEAT_CVT");
+  m->feat_cvt = env != nullptr && env[0] == '1';
   env = getenv("VC_EARLY_ATTN");
   m->early_attn = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_EARLY_Q");

@@ -258,6 +258,8 @@ struct TcArgs {
   const unsigned int* sync_wait;
   unsigned int sync_target;
   int sync_row_shift;     // gemm_tc_kernel: counter index = m0 >> sync_row_shift
+  const float* a32;       // CVT kernels: the fp32 A operand [M, lda32] (converted to bf16 by the producer warps)
+  int64_t lda32;
 };
 
 // ---------------------------------------------------------------- the kernel
@@ -583,9 +585,10 @@ __device__ __forceinline__ uint64_t fma_f2(uint64_t a, uint64_t b, uint64_t c) {
   return r;
 }
 
-template <int EPI> struct PersistentCfg {
+template <int EPI, bool CVT = false> struct PersistentCfg {
   static constexpr int kEpiWarps = (EPI == EPI_STORE) ? 8 : 4;
-  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kCvtWarps = CVT ? 16 : 0;          // fp32 -> bf16 converting A producers (CVT)
+  static constexpr int kThreads = 64 + 32 * kEpiWarps + 32 * kCvtWarps;
 };
 
 // TF32: the operands in memory are fp32 (read by the tensor cores as tf32); a k-block is still 128 bytes per row,
@@ -595,12 +598,18 @@ template <int EPI> struct PersistentCfg {
 // same n-tile; both producers signal the leader's full barrier, the leader's MMA completions release the ring slot and
 // publish the accumulator in both CTAs, and both epilogues hand the accumulator back on the leader's barrier
 // (maps.W[1]: W with a 128-row box).
-template <int kStages, int EPI, class OutT, bool TANH, bool STATS, bool TF32 = false, bool MC = false>
-__global__ void __launch_bounds__(PersistentCfg<EPI>::kThreads, 1)
+// CVT: A is fp32 in global memory and is NOT staged by TMA: 16 converter warps load it with ld.global.nc (three k-blocks in
+// flight in registers), round to bf16 and write the 128B-swizzled A tile of the ring themselves (fence.proxy.async before
+// the arrive: the MMA reads shared memory through the async proxy).  The feature projection then runs at the bf16 MMA rate
+// instead of the tf32 one without a separate conversion pass; a conversion THROUGH shared memory would need ~250 B/clk of
+// the SM's 128 B/clk.  EPI_STORE, single CTA, no STATS.
+template <int kStages, int EPI, class OutT, bool TANH, bool STATS, bool TF32 = false, bool MC = false, bool CVT = false>
+__global__ void __launch_bounds__(PersistentCfg<EPI, CVT>::kThreads, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, const int tiles_m, const int tiles_n,
                           const VocabStats vstat) {
   static_assert(!STATS || (EPI == EPI_STORE && sizeof(OutT) == 4 && !TANH), "STATS: fp32 logits store only");
   static_assert(!TF32 || (EPI == EPI_STORE && !STATS), "TF32 operands: plain store epilogue only");
+  static_assert(!CVT || (EPI == EPI_STORE && !STATS && !TF32 && !MC), "CVT: plain store epilogue, single CTA, bf16 MMA");
   constexpr int BN = 256;
   constexpr int BKE = TF32 ? 32 : BK;              // elements per k-block (128 bytes per row)
   constexpr int kEpiThreads = 32 * PersistentCfg<EPI>::kEpiWarps;
@@ -633,7 +642,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), 1 + PersistentCfg<EPI, CVT>::kCvtWarps);   // W producer (+ one arrival per converter warp)
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -666,7 +675,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
   };
   // the barrier of a slot is armed once per use, by the leader, for both CTAs' bytes
   auto arm = [&](uint32_t fb) {
-    if (!MC) mbar_expect_tx(fb, kStageBytes);
+    if (CVT) mbar_expect_tx(fb, kBBytes);                  // the A half of the slot is written by the converter warps
+    else if (!MC) mbar_expect_tx(fb, kStageBytes);
     else if (crank == 0) mbar_expect_tx(fb, 2 * kStageBytes);
   };
   // an epilogue thread is done with accumulator a: tell the MMA issuer (MC: the leader's barrier, from either CTA)
@@ -719,7 +729,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           const int k = kb * BKE;
           const int acol = g.a_col0[0] + k + (k >= g.a_split ? g.a_skip : 0);
           uint8_t* sa = smem + (size_t)stage * kStageBytes;
-          load_a(sa, fb, acol, m0);
+          if (!CVT) load_a(sa, fb, acol, m0);
           if (!pre) load_w(sa + kABytes, fb, k, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -766,6 +776,57 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         if (MC) umma_commit_2sm(smem_u32(&tmem_full[a]));           // accumulator halves complete in both CTAs
         else umma_commit(smem_u32(&tmem_full[a]));
       }
+    }
+  } else if (CVT && warp >= 2 + PersistentCfg<EPI, CVT>::kEpiWarps) {
+    // ===== fp32 -> bf16 converting A producers: thread = (row, 16-float quarter of the 64-element k-block) =====
+    const int ct = (int)threadIdx.x - 32 * (2 + PersistentCfg<EPI, CVT>::kEpiWarps);   // 0..511
+    const int crow = ct >> 2, cq = ct & 3;
+    int l_tile = t_first, l_kb = 0;                        // next (tile, k-block) of the load stream
+    auto issue = [&](uint4 (&b)[4]) {
+      if (l_tile < t_last) {
+        const int row = (l_tile / tiles_n) * BM + crow;
+        if (row < g.M) {
+          const float* p = g.a32 + (size_t)row * g.lda32 + (size_t)l_kb * BK + cq * 16;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(b[i].x), "=r"(b[i].y), "=r"(b[i].z), "=r"(b[i].w) : "l"(p + 4 * i));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) b[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (++l_kb == nkb) { l_kb = 0; l_tile += t_step; }
+      }
+    };
+    uint32_t stage = 0, phase = 0;
+    auto consume = [&](const uint4 (&b)[4]) {
+      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+      const uint32_t sa = smem_u32(smem + (size_t)stage * kStageBytes);
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        w[2 * i] = pack_bf16(__uint_as_float(b[i].x), __uint_as_float(b[i].y));
+        w[2 * i + 1] = pack_bf16(__uint_as_float(b[i].z), __uint_as_float(b[i].w));
+      }
+      sts128(swz(sa, crow, 2 * cq), w[0], w[1], w[2], w[3]);
+      sts128(swz(sa, crow, 2 * cq + 1), w[4], w[5], w[6], w[7]);
+      fence_proxy_async_smem();                            // generic-proxy writes -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(smem_u32(&full_bar[stage]));
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    };
+    int n_mine = 0;
+    for (int tile = t_first; tile < t_last; tile += t_step) ++n_mine;
+    const int total = n_mine * nkb;
+    uint4 b0[4], b1[4], b2[4];
+    issue(b0);
+    issue(b1);
+    issue(b2);
+    for (int j = 0; j < total; j += 3) {
+      consume(b0);
+      issue(b0);
+      if (j + 1 < total) { consume(b1); issue(b1); }
+      if (j + 2 < total) { consume(b2); issue(b2); }
     }
   } else {
     // ===== epilogue =====
@@ -1433,6 +1494,37 @@ inline int launch_gemm_tc_tf32(const GemmArgs& g, int64_t a_cols, const EpiStore
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VC_CUDA(launch_pdl(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem, stream, mp, ta, tm, tn, vs));
   }
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ---- fp32 A converted to bf16 by the kernel's producer warps (feature projection): C[M,N] bf16 = bf16(A[M,K] fp32) . W[N,K]^T bf16 + bias
+inline int launch_gemm_tc_cvt(const float* A32, int64_t lda32, const void* Wbf16, int64_t ldw, int M, int N, int K,
+                              const EpiStore<bf16, false, false>& e, cudaStream_t stream) {
+  if (M == 0 || N == 0) return VC_OK;
+  VC_CHECK(e.C2[0] == nullptr && tma_ok(e.C[0], e.ldc, 2) && tma_ok(Wbf16, ldw, 2) && N >= 256 && K % BK == 0 &&
+               (reinterpret_cast<uintptr_t>(A32) & 15) == 0 && lda32 % 4 == 0,
+           "converting GEMM: unsupported operand layout");
+  TcMaps mp;
+  TcArgs ta;
+  memset(&ta, 0, sizeof(ta));
+  memset(&mp, 0, sizeof(mp));
+  ta.M = M; ta.N = N; ta.K = K; ta.a_split = 1 << 30;
+  ta.a32 = A32; ta.lda32 = lda32;
+  ta.bias[0] = ta.bias[1] = e.bias[0];
+  VC_TRY(get_map(&mp.W[0], Wbf16, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 256u, 2));
+  mp.W[1] = mp.W[0];
+  mp.A[0] = mp.A[1] = mp.W[0];        // never loaded through (only prefetched in the prologue)
+  VC_TRY(get_map(&mp.io[0], e.C[0], (uint64_t)M, (uint64_t)N, (uint64_t)e.ldc, BM, 2));
+  constexpr int kStages = 3;
+  const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 4 * kBoxBytes + 1024;
+  const int tm = (M + BM - 1) / BM, tn = (N + 255) / 256;
+  const int ctas = tm * tn < num_sms() ? tm * tn : num_sms();
+  VocabStats vs;
+  memset(&vs, 0, sizeof(vs));
+  auto kern = gemm_tc_persistent_kernel<kStages, EPI_STORE, bf16, false, false, false, false, true>;
+  VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VC_CUDA(launch_pdl(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE, true>::kThreads), smem, stream, mp, ta, tm, tn, vs));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
