@@ -778,22 +778,24 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       }
     }
   } else if (CVT && warp >= 2 + PersistentCfg<EPI, CVT>::kEpiWarps) {
-    // ===== fp32 -> bf16 converting A producers: thread = (row, 16-float quarter of the 64-element k-block) =====
-    const int ct = (int)threadIdx.x - 32 * (2 + PersistentCfg<EPI, CVT>::kEpiWarps);   // 0..511
-    const int crow = ct >> 2, cq = ct & 3;
+    // ===== fp32 -> bf16 converting A producers =====
+    // Lane mapping: a warp instruction reads two whole 256-byte row segments (lanes 0-15 row r, lanes 16-31 row r+1), so every
+    // 32-byte sector is fetched once; a warp owns 8 rows of the tile (4 instructions), a thread 4 floats of each of 4 rows.
+    const int cw = warp - (2 + PersistentCfg<EPI, CVT>::kEpiWarps);      // 0..15
+    const int lrow = lane >> 4, lcol = lane & 15;                        // row parity inside an instruction, 16-byte column
     int l_tile = t_first, l_kb = 0;                        // next (tile, k-block) of the load stream
     auto issue = [&](uint4 (&b)[4]) {
       if (l_tile < t_last) {
-        const int row = (l_tile / tiles_n) * BM + crow;
-        if (row < g.M) {
-          const float* p = g.a32 + (size_t)row * g.lda32 + (size_t)l_kb * BK + cq * 16;
+        const int row0 = (l_tile / tiles_n) * BM + cw * 8 + lrow;
+        const float* p = g.a32 + (size_t)row0 * g.lda32 + (size_t)l_kb * BK + lcol * 4;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) {
+          if (row0 + 2 * i < g.M) {
             asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(b[i].x), "=r"(b[i].y), "=r"(b[i].z), "=r"(b[i].w) : "l"(p + 4 * i));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) b[i] = make_uint4(0u, 0u, 0u, 0u);
+                         : "=r"(b[i].x), "=r"(b[i].y), "=r"(b[i].z), "=r"(b[i].w) : "l"(p + (size_t)(2 * i) * g.lda32));
+          } else {
+            b[i] = make_uint4(0u, 0u, 0u, 0u);
+          }
         }
         if (++l_kb == nkb) { l_kb = 0; l_tile += t_step; }
       }
@@ -802,14 +804,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
     auto consume = [&](const uint4 (&b)[4]) {
       mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
       const uint32_t sa = smem_u32(smem + (size_t)stage * kStageBytes);
-      uint32_t w[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        w[2 * i] = pack_bf16(__uint_as_float(b[i].x), __uint_as_float(b[i].y));
-        w[2 * i + 1] = pack_bf16(__uint_as_float(b[i].z), __uint_as_float(b[i].w));
+        const int r = cw * 8 + 2 * i + lrow;               // row inside the tile
+        const uint32_t w0 = pack_bf16(__uint_as_float(b[i].x), __uint_as_float(b[i].y));
+        const uint32_t w1 = pack_bf16(__uint_as_float(b[i].z), __uint_as_float(b[i].w));
+        // 4 bf16 = 8 bytes: half of 16-byte chunk lcol/2 of the 128B-swizzled row
+        const uint32_t addr = swz(sa, r, lcol >> 1) + (uint32_t)(lcol & 1) * 8u;
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(w0), "r"(w1) : "memory");
       }
-      sts128(swz(sa, crow, 2 * cq), w[0], w[1], w[2], w[3]);
-      sts128(swz(sa, crow, 2 * cq + 1), w[4], w[5], w[6], w[7]);
       fence_proxy_async_smem();                            // generic-proxy writes -> visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive_cta(smem_u32(&full_bar[stage]));
