@@ -228,12 +228,22 @@ class CaptionOracle:
         return out
 
     # ------------------------------------------------------------------ beam (a9), B=1 semantics
-    def _beam_one(self, enc_out, final, mask, start_id, end_id, max_length, K, length_penalty):
+    def _beam_one(self, enc_out, final, mask, start_id, end_id, max_length, K, length_penalty, diverse=False):
         """_beam_search_generate for ONE video, video_captioning_model.py:148-302.
 
         Restates the reference literally for batch_size == 1 (the only well-defined case,
         SURVEY.md section 3.3): scores start at ZERO for all K beams (:194) so all beams tie.
-        Returns (tokens incl. leading START, per-step top score list).
+
+        ``diverse=True`` is the repair the reference itself asks for (inference/predictor.py:353 "modify beam
+        search to return multiple hypotheses"): the SAME loop with ``scores[1:] = -inf`` at step 0, so the K
+        rows stop being copies of each other; completed hypotheses go to a per-video list with the
+        length-normalised score of :237-242, which now matters.  Nothing else changes.
+
+        Returns a dict: ``best`` (tokens incl. leading START), ``best_score`` (normalised score of the best
+        completed hypothesis, else the raw score of live beam 0, :274-286), ``step_scores`` (per-step top-K
+        candidate scores), ``nbest`` = [(tokens, score)]: completed hypotheses by normalised score
+        (descending, first-completed first among equals -- what ``max`` at :277-281 keeps), followed by the
+        beams still live after ``max_length`` steps (score / generated_length ** length_penalty).
         """
         V = self.V
         enc = enc_out.expand(K, -1, -1).contiguous()                          # :179-181
@@ -241,9 +251,12 @@ class CaptionOracle:
         pre = tuple(t.expand(K, -1, -1).contiguous() for t in self.precompute_keys(enc_out))
         seqs = torch.full((K, 1), start_id, dtype=torch.long)                 # :191-193
         scores = torch.zeros(K, dtype=self.dtype)                             # :194
+        if diverse:
+            scores[1:] = float("-inf")
         state = self.init_hidden(final.expand(K, -1).contiguous())            # :196
         completed: List[Tuple[torch.Tensor, float]] = []
         step_scores = []
+        live = True
         for _ in range(max_length):                                           # :202
             R = seqs.shape[0]
             logits, state, _ = self.forward_step(seqs[:, -1], state, enc[:R], msk[:R], tuple(t[:R] for t in pre))
@@ -265,42 +278,72 @@ class CaptionOracle:
                     new_scores.append(top_s[0, k])
                     keep.append(ob)
             if not new_seqs:                                                  # :251
+                live = False
                 break
             seqs = torch.stack(new_seqs)                                      # :254-266 (equal lengths for B=1)
             scores = torch.stack(new_scores)                                  # :267
             idx = torch.tensor(keep)
             state = (state[0][:, idx].clone(), state[1][:, idx].clone())      # :269-272
         if completed:                                                         # :274-282
-            best = max(completed, key=lambda x: x[1])[0]
+            best, best_score = max(completed, key=lambda x: x[1])
         else:
-            best = seqs[0]                                                    # :286
-        return best, step_scores
+            best, best_score = seqs[0], float(scores[0])                      # :286
+        nbest = sorted(completed, key=lambda x: -x[1])                        # stable: first-completed first among equals
+        if live:
+            gen = seqs.shape[1] - 1
+            nbest += [(seqs[k], float(scores[k]) / (gen ** length_penalty)) for k in range(seqs.shape[0])]
+        return {"best": best, "best_score": best_score, "step_scores": step_scores, "nbest": nbest}
 
     def beam(self, feats, start_id, end_id, max_length=20, mask=None, beam_size=5, length_penalty=1.0,
-             return_scores=False) -> Dict[str, torch.Tensor]:
+             return_scores=False, diverse=False, num_return=0) -> Dict[str, torch.Tensor]:
         """Batched contract: row i == the reference's B=1 call on video i
-        (predictor.py:102 always calls with B=1); rows right-padded with START (:288-300)."""
+        (predictor.py:102 always calls with B=1); rows right-padded with START (:288-300).
+        ``num_return`` > 0 adds the n-best lists (see _beam_one): ``nbest_tokens`` [B,N,L] START-padded,
+        ``nbest_lengths`` [B,N] (0 = no such hypothesis), ``nbest_scores`` [B,N] (-inf there)."""
         feats = torch.as_tensor(feats)
         enc_out, final = self.encode(feats, mask)
         B = feats.shape[0]
         if mask is None:
             mask = torch.ones(B, feats.shape[1], dtype=self.dtype)
-        rows, sc = [], []
-        for b in range(B):
-            best, ss = self._beam_one(enc_out[b:b + 1], final[b:b + 1], mask[b:b + 1], start_id, end_id,
-                                      max_length, beam_size, length_penalty)
-            rows.append(best)
-            sc.append(ss)
+        res1 = [self._beam_one(enc_out[b:b + 1], final[b:b + 1], mask[b:b + 1], start_id, end_id,
+                               max_length, beam_size, length_penalty, diverse) for b in range(B)]
+        rows = [r["best"] for r in res1]
         L = max(len(r) for r in rows)
         out = torch.full((B, L), start_id, dtype=torch.long)
         lens = torch.zeros(B, dtype=torch.long)
         for b, r in enumerate(rows):
             out[b, : len(r)] = r
             lens[b] = len(r)
-        res = {"generated_tokens": out, "lengths": lens}
+        res = {"generated_tokens": out, "lengths": lens,
+               "scores": torch.tensor([r["best_score"] for r in res1], dtype=torch.float64)}
         if return_scores:
-            res["step_scores"] = sc
+            res["step_scores"] = [r["step_scores"] for r in res1]
+        if num_return > 0:
+            N = num_return
+            nt = torch.full((B, N, max_length + 1), start_id, dtype=torch.long)
+            nl = torch.zeros(B, N, dtype=torch.long)
+            nsc = torch.full((B, N), float("-inf"), dtype=torch.float64)
+            for b, r in enumerate(res1):
+                for j, (t, sc) in enumerate(r["nbest"][:N]):
+                    nt[b, j, : len(t)] = t
+                    nl[b, j] = len(t)
+                    nsc[b, j] = sc
+            res.update(nbest_tokens=nt, nbest_lengths=nl, nbest_scores=nsc)
         return res
+
+    def sequence_logprob(self, feats, tokens, lengths, mask=None) -> torch.Tensor:
+        """Sum of log-softmax probabilities of given START-prefixed rows (teacher-forced through
+        forward_step): the un-normalised beam score of video_captioning_model.py:209-213 for a FIXED token
+        sequence.  tokens [B,L] (index 0 = START), lengths [B] (incl. START) -> [B] float64."""
+        tokens = torch.as_tensor(tokens).long()
+        lengths = torch.as_tensor(lengths).long()
+        n = int(lengths.max()) - 1
+        lg = self.forward_teacher(feats, tokens[:, :n], mask)["logits"]
+        lp = torch.log_softmax(lg.double(), dim=-1)
+        tgt = tokens[:, 1:n + 1]
+        g = lp.gather(2, tgt.unsqueeze(-1)).squeeze(-1)
+        valid = torch.arange(n)[None, :] < (lengths - 1)[:, None]
+        return (g * valid).sum(dim=1)
 
     # ------------------------------------------------------------------ teacher forcing (f1)
     def forward_teacher(self, feats, input_tokens, mask=None) -> Dict[str, torch.Tensor]:

@@ -24,6 +24,14 @@ def load_golden(name):
     return g
 
 
+def diverse_golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "diverse", "*.npz")))
+
+
+def load_diverse_golden(name):
+    return load_golden(os.path.join("diverse", name))
+
+
 def build_inputs(rc):
     cfg = synth.make_config(rc["shape"])
     V = cfg.model.vocab_size

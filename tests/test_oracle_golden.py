@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 import torch
 
-from _util import END, START, build_inputs, golden_names, load_golden, make_oracle
+from _util import (END, START, build_inputs, diverse_golden_names, golden_names, load_diverse_golden, load_golden,
+                   make_oracle)
 
 NAMES = golden_names()
 FAST = [n for n in NAMES if not n.startswith(("msvd", "c4"))]
@@ -58,3 +59,47 @@ def test_fp64_oracle_close_to_fp32():
     o64 = make_oracle(sd, dtype=torch.float64)
     tf = o64.forward_teacher(torch.from_numpy(feats).double(), g["tf_input_tokens"])
     np.testing.assert_allclose(tf["logits"].numpy(), g["tf_logits"], rtol=0, atol=2e-5)
+
+
+# ------------------------------------------------------------------ real ("diverse") beam search, SURVEY 8f rank 3
+DIVERSE = diverse_golden_names()
+
+
+@pytest.mark.parametrize("name", [n for n in DIVERSE if not n.startswith(("msvd", "c4"))])
+def test_oracle_diverse_beam_matches_repaired_reference(name):
+    """oracle.beam(diverse=True) against the unmodified reference loop run with scores[1:] = -inf
+    (oracle/make_golden_diverse.py, ref_shim.reference_diverse_beam): same best hypothesis per video."""
+    g = load_diverse_golden(name)
+    rc = g["recipe"]
+    cfg, V, sd, feats = build_inputs(rc)
+    bm = make_oracle(sd).beam(feats, START, END, max_length=rc["S"], beam_size=rc["K"], length_penalty=rc["lp"],
+                              diverse=True, num_return=rc["K"])
+    assert np.array_equal(bm["lengths"].numpy(), g["beam_lengths"])
+    assert np.array_equal(bm["generated_tokens"].numpy(), g["beam_tokens"])
+    # n-best list: entry 0 is the returned hypothesis; completed hypotheses come sorted by normalised score
+    nt, nl, ns = bm["nbest_tokens"].numpy(), bm["nbest_lengths"].numpy(), bm["nbest_scores"].numpy()
+    for b in range(rc["B"]):
+        n0 = int(nl[b, 0])
+        assert nt[b, 0, :n0].tolist() == g["beam_tokens"][b, :n0].tolist()
+        done = [j for j in range(rc["K"]) if nl[b, j] > 0 and nt[b, j, nl[b, j] - 1] == END]
+        assert done == list(range(len(done))), "completed hypotheses precede live ones"
+        assert all(ns[b, j] >= ns[b, j + 1] for j in range(len(done) - 1))
+        rows = {tuple(nt[b, j, : nl[b, j]].tolist()) for j in range(rc["K"]) if nl[b, j] > 0}
+        assert len(rows) == int((nl[b] > 0).sum()), "hypotheses are distinct"
+
+
+def test_oracle_sequence_logprob_equals_beam_score():
+    """The score the beam reports for its best hypothesis is the (length-normalised) sum of the log-probabilities
+    of its tokens: sequence_logprob re-derives it teacher-forced."""
+    g = load_diverse_golden("tiny_bahdanau_k5")
+    rc = g["recipe"]
+    cfg, V, sd, feats = build_inputs(rc)
+    o = make_oracle(sd)
+    bm = o.beam(feats, START, END, max_length=rc["S"], beam_size=rc["K"], length_penalty=rc["lp"], diverse=True)
+    lp = o.sequence_logprob(feats, bm["generated_tokens"], bm["lengths"])
+    toks, lens = bm["generated_tokens"], bm["lengths"]
+    for b in range(rc["B"]):
+        n = int(lens[b]) - 1
+        ended = int(toks[b, n]) == END
+        exp = float(lp[b]) / (n ** rc["lp"]) if ended else float(lp[b])
+        assert abs(exp - float(bm["scores"][b])) < 1e-4 * max(1.0, abs(exp))

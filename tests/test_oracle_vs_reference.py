@@ -49,3 +49,18 @@ def test_live_vocabulary_and_resize():
     idx = torch.linspace(0, 199, 80, dtype=torch.long)
     assert np.array_equal(resize_features(x, 80), x[idx.numpy()])
     assert resize_features(x[:10], 16).shape == (16, 3) and resize_features(x[:10], 16)[10:].sum() == 0
+
+
+@pytest.mark.parametrize("att", synth.ATTENTION_TYPES)
+def test_live_diverse_beam(att):
+    """Real beam search: oracle.beam(diverse=True) vs the unmodified reference loop with scores[1:] = -inf."""
+    cfg = synth.make_config("tiny")
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, att, seed=33, logit_gain=4.0, end_token_id=2, end_bias=0.3)
+    ref = ref_shim.build_reference_model(cfg, V, att, state_dict=sd)
+    o = CaptionOracle(sd)
+    x = torch.from_numpy(synth.make_features(3, 16, 256, seed=34, kind="ragged"))
+    q = o.beam(x, 1, 2, max_length=10, beam_size=4, length_penalty=1.2, diverse=True)
+    for b in range(3):
+        r = ref_shim.reference_diverse_beam(ref, x[b:b + 1], 1, 2, 10, 4, 1.2)
+        assert r.tolist() == q["generated_tokens"][b, : int(q["lengths"][b])].tolist()
