@@ -7,9 +7,13 @@
  * calls it through ctypes.  INTEGRATION.md shows the binding a reference maintainer would add.
  *
  * Conventions: plain C, raw device pointers + cudaStream_t, caller-allocated outputs and workspace,
- * int status codes (0 = ok; no exceptions or aborts cross the ABI), thread-compatible (one handle per
- * thread).  All float tensors are fp32 row-major; token ids are int32.  Paths below are relative to
- * the reference's src/ directory.
+ * int status codes (0 = ok; no exceptions or aborts cross the ABI), thread-compatible: a handle and its
+ * workspace are driven by one thread at a time, different handles may be used from different threads
+ * (vc_last_error is thread-local; the launch counter is atomic and the vc_profile_* bookkeeping, which is
+ * process-global, is mutex-guarded; the VC_* environment switches are read with getenv and must not be
+ * changed with setenv concurrently).  All float tensors are fp32 row-major; token ids are int32.  Sizes:
+ * F, H, E, A multiples of 8 (64 in VC_PREC_BF16 mode: tensor-core tiles), any vocabulary size >= 4 (padded
+ * internally).  Paths below are relative to the reference's src/ directory.
  */
 #ifndef VC_B200_H_
 #define VC_B200_H_
@@ -123,6 +127,16 @@ int vc_decode_greedy(vc_model_t* m, int32_t B, int32_t T, const float* mask, con
 int vc_decode_beam(vc_model_t* m, int32_t B, int32_t T, const float* mask, const vc_decode_params_t* p,
                    int32_t* tokens, int32_t* lengths, float* scores, void* workspace, size_t workspace_bytes,
                    vc_stream_t stream);
+
+/* ---- n-best list of the beam decode that last ran in `workspace` (same B, T and *p): what
+ * generate_multiple_captions wants from the beam ("modify beam search to return multiple hypotheses",
+ * inference/predictor.py:353; semantics of video_captioning_model.py:237-242, :274-286).  Per video: the completed
+ * hypotheses by length-normalised score (descending; entry 0 is the hypothesis vc_decode_beam returned), then the beams
+ * still live after max_length steps with score / max_length^length_penalty.  tokens [B,N,S+1] (index 0 = START,
+ * START-padded), lengths [B,N] (incl. START; 0 = no such hypothesis), scores [B,N] (-inf there).  1 <= N <= 2*beam_size.
+ * Meaningful with diverse_beams = 1 (under reference semantics all K hypotheses are copies of each other). */
+int vc_beam_nbest(vc_model_t* m, int32_t B, int32_t T, const vc_decode_params_t* p, int32_t N, int32_t* tokens,
+                  int32_t* lengths, float* scores, void* workspace, size_t workspace_bytes, vc_stream_t stream);
 
 /* ---- VideoCaptioningModel.generate (video_captioning_model.py:79-125): encoder + precompute + decode.
  * tokens is [B,S] (greedy) or [B,S+1] (beam); lengths/scores/attn_weights may be NULL. */

@@ -42,7 +42,12 @@ def test_create_rejects_bad_descriptors():
     st = lib.vc_decode_greedy(h, 1, 16, None, ctypes.byref(p), ctypes.c_void_p(8), None, ctypes.c_void_p(8), 1 << 40, None)
     assert st == 1 and b"finalized" in lib.vc_last_error()
     lib.vc_model_destroy(h)
-    for bad in (dict(hidden_dim=100), dict(vocab_size=1001), dict(enc_layers=9), dict(precision=7),
+    # any vocabulary size is accepted (padded internally): reference checkpoints have V = len(vocabulary)
+    d = _native.ModelDesc(**{**good, "vocab_size": 1001})
+    h = ctypes.c_void_p()
+    assert lib.vc_model_create(ctypes.byref(d), ctypes.byref(h)) == 0
+    lib.vc_model_destroy(h)
+    for bad in (dict(hidden_dim=100), dict(vocab_size=3), dict(enc_layers=9), dict(precision=7),
                 dict(attention=4, num_heads=7), dict(precision=1, embed_dim=40)):
         d = _native.ModelDesc(**{**good, **bad})
         h = ctypes.c_void_p()

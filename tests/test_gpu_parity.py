@@ -513,3 +513,318 @@ def test_fused_select_equals_streaming_select(monkeypatch, shape, V, B, K):
     assert torch.equal(t0, t1) and torch.equal(l0, l1) and torch.equal(g0, g1)
     if s0 is not None:
         assert torch.allclose(s0, s1, rtol=1e-5, atol=1e-5)     # log-sum-exp merged in a different order
+
+
+# ------------------------------------------------------------------ real ("diverse") beam search + n-best
+def _check_nbest_structure(out, K):
+    nl = out["nbest_lengths"].cpu()
+    ns = out["nbest_scores"].cpu()
+    assert torch.equal(out["nbest_tokens"][:, 0, : out["generated_tokens"].shape[1]].cpu(),
+                       out["generated_tokens"].cpu()[:, : out["nbest_tokens"].shape[2]])
+    assert torch.equal(nl[:, 0], out["lengths"].cpu())
+    assert (ns[nl == 0] == float("-inf")).all()
+
+
+@pytest.mark.parametrize("name", __import__("_util").diverse_golden_names())
+def test_diverse_beam_fp32_vs_reference_and_oracle(name):
+    """First test in which the beam parents are NOT the identity: scores[1:] = -inf at step 0 (the repair the reference
+    asks for, predictor.py:353), so the K rows of a video diverge, get reordered every step (reorder_embed_kernel, the
+    attention kernels' q_rows indirection, token-history copies, live-beam compaction) and finish at different steps.
+    fp32: best hypothesis == the unmodified reference loop's (golden), whole n-best list == the oracle's (tokens and
+    lengths identical, scores within 1e-3)."""
+    from _util import load_diverse_golden
+    g = load_diverse_golden(name)
+    rc = g["recipe"]
+    cfg, V, sd, feats = build_inputs(rc)
+    K, S = rc["K"], rc["S"]
+    ref = make_oracle(sd).beam(feats, START, END, max_length=S, beam_size=K, length_penalty=rc["lp"], diverse=True,
+                               num_return=2 * K)
+    m = make_native_model(cfg, V, sd, rc["attention"], "fp32")
+    x = torch.from_numpy(feats).cuda()
+    out = m.generate(x, START, END, max_length=S, method="beam", beam_size=K, length_penalty=rc["lp"], diverse_beams=True,
+                     num_return_sequences=2 * K)
+    L = g["beam_tokens"].shape[1]
+    assert np.array_equal(out["lengths"].cpu().numpy(), g["beam_lengths"])
+    assert np.array_equal(out["generated_tokens"].cpu().numpy()[:, :L], g["beam_tokens"]), "best hypothesis differs from the reference"
+    assert rel_err(out["scores"].cpu(), ref["scores"]) < FP32_LOGIT_TOL
+    _check_nbest_structure(out, K)
+    nl = out["nbest_lengths"].cpu()
+    assert torch.equal(nl, ref["nbest_lengths"]), (nl, ref["nbest_lengths"])
+    Ln = out["nbest_tokens"].shape[2]
+    assert torch.equal(out["nbest_tokens"].cpu(), ref["nbest_tokens"][:, :, :Ln])
+    have = nl > 0
+    a, b = out["nbest_scores"].cpu().double()[have], ref["nbest_scores"][have]
+    assert float(((a - b).abs() / b.abs().clamp_min(1e-6)).max()) < FP32_LOGIT_TOL
+    assert (nl > 0).sum(1).min() >= K          # at least K hypotheses per video
+
+
+@pytest.mark.parametrize("name", ["tiny_bahdanau_k5", "tiny_luong_general_k3", "tiny_luong_dot_k3", "tiny_luong_concat_k5",
+                                  "tiny_multihead_k3", "small_bahdanau_k5", "msvd_bahdanau_k5", "c4_multihead_k3"])
+def test_diverse_beam_bf16_scores_vs_oracle(name):
+    """bf16 free-running diverse beam: tokens cannot be compared (near-ties flip), but every reported score must be the
+    length-normalised sum of log-probabilities of the reported tokens: the oracle re-derives it teacher-forced (fp32) over
+    the GPU's own hypotheses -- best and n-best -- within the bf16 bar (2e-2 relative)."""
+    from _util import load_diverse_golden
+    g = load_diverse_golden(name)
+    rc = g["recipe"]
+    cfg, V, sd, feats = build_inputs(rc)
+    K, S, lp = rc["K"], rc["S"], rc["lp"]
+    o = make_oracle(sd)
+    m = make_native_model(cfg, V, sd, rc["attention"], "bf16")
+    x = torch.from_numpy(feats).cuda()
+    out = m.generate(x, START, END, max_length=S, method="beam", beam_size=K, length_penalty=lp, diverse_beams=True,
+                     num_return_sequences=K)
+    _check_nbest_structure(out, K)
+    nt, nl, ns = out["nbest_tokens"].cpu(), out["nbest_lengths"].cpu(), out["nbest_scores"].cpu().double()
+    B = nt.shape[0]
+    for j in range(K):
+        rows = [b for b in range(B) if nl[b, j] > 0]
+        if not rows:
+            continue
+        lpo = o.sequence_logprob(feats[rows], nt[rows, j], nl[rows, j])
+        n = (nl[rows, j] - 1).double()
+        exp = lpo / n.pow(lp)            # completed (score/(len-1)^lp) and live-at-the-end hypotheses (same formula)
+        got = ns[rows, j]
+        assert float(((got - exp).abs() / exp.abs()).max()) < BF16_LOGIT_TOL, (name, j, got, exp)
+    # hypotheses of a video are distinct
+    for b in range(B):
+        rows = {tuple(nt[b, j, : nl[b, j]].tolist()) for j in range(K) if nl[b, j] > 0}
+        assert len(rows) == int((nl[b] > 0).sum())
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_reference_beam_scores_vs_oracle(name):
+    """Reference-mode beam (all scores start at 0): the returned score is compared with the oracle's (normalised score of
+    the best completed hypothesis, else raw score of live beam 0) -- fp32 within 1e-3, bf16 against the oracle's
+    log-probability of the GPU's own tokens within 2e-2."""
+    g = load_golden(name)
+    rc = g["recipe"]
+    cfg, V, sd, feats = build_inputs(rc)
+    o = make_oracle(sd)
+    ref = o.beam(feats, START, END, max_length=rc["S"], beam_size=rc["K"], length_penalty=1.0)
+    x = torch.from_numpy(feats).cuda()
+    out = make_native_model(cfg, V, sd, rc["attention"], "fp32").generate(x, START, END, max_length=rc["S"], method="beam",
+                                                                         beam_size=rc["K"])
+    assert rel_err(out["scores"].cpu(), ref["scores"]) < FP32_LOGIT_TOL
+    out = make_native_model(cfg, V, sd, rc["attention"], "bf16").generate(x, START, END, max_length=rc["S"], method="beam",
+                                                                         beam_size=rc["K"])
+    t, l = out["generated_tokens"].cpu(), out["lengths"].cpu()
+    lpo = o.sequence_logprob(feats, t, l)
+    ended = t[torch.arange(t.shape[0]), l - 1] == END
+    exp = torch.where(ended, lpo / (l - 1).double(), lpo)
+    assert float(((out["scores"].cpu().double() - exp).abs() / exp.abs()).max()) < BF16_LOGIT_TOL
+
+
+# ------------------------------------------------------------------ the benchmarked configuration against the oracle
+def test_benchmark_configuration_vs_oracle():
+    """B=1024 MSVD-shape videos, beam 5, bf16, every default switch on (CTA-pair GEMMs, tile hand-over, STATS vocabulary
+    epilogue + shared threshold, early query projection, persistent attention v5, persistent encoder recurrence): sampled
+    rows against the oracle -- encoder outputs and teacher-forced logits within 2e-2, and the free-running beam's reported
+    scores against the oracle's log-probability of the GPU's own tokens within 2e-2, in reference and in diverse mode."""
+    from oracle import synth
+    cfg = synth.make_config("msvd")
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, "bahdanau", seed=0, logit_gain=8.0, end_token_id=END, end_bias=0.45)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(1024, 80, 4096, generator=g, device="cuda")
+    rows = [0, 255, 511, 1023]
+    xs = x[rows].cpu()
+    o = make_oracle(sd)
+    m = make_native_model(cfg, V, sd, "bahdanau", "bf16")
+    S = 20
+    gt = o.greedy(xs, START, END, max_length=S)["generated_tokens"]
+    inp_s = torch.cat([torch.full((4, 1), START), gt[:, :-1]], 1)
+    tf_o = o.forward_teacher(xs, inp_s)
+    inp = torch.randint(4, V, (1024, inp_s.shape[1]), generator=torch.Generator().manual_seed(1))
+    inp[:, 0] = START
+    inp[rows] = inp_s
+    tf = m(x, inp.cuda(), None)
+    assert rel_err(tf["logits"][rows].cpu(), tf_o["logits"]) < BF16_LOGIT_TOL
+    assert rel_err(tf["encoder_outputs"][rows].cpu(), tf_o["encoder_outputs"]) < BF16_LOGIT_TOL
+    assert np.abs(tf["attention_weights"][rows].cpu().numpy() - tf_o["attention_weights"].numpy()).max() < 2e-2
+    del tf
+    for diverse in (False, True):
+        out = m.generate(x, START, END, max_length=S, method="beam", beam_size=5, diverse_beams=diverse, num_return_sequences=5)
+        t, l, sc = out["generated_tokens"].cpu(), out["lengths"].cpu(), out["scores"].cpu().double()
+        assert len(set(l.tolist())) > 1
+        lpo = o.sequence_logprob(xs, t[rows], l[rows])
+        ll = l[rows]
+        ended = t[rows][torch.arange(4), ll - 1] == END
+        exp = torch.where(ended, lpo / (ll - 1).double(), lpo)
+        assert float(((sc[rows] - exp).abs() / exp.abs()).max()) < BF16_LOGIT_TOL, (diverse, sc[rows], exp)
+        if diverse:
+            nt, nl, ns = out["nbest_tokens"].cpu(), out["nbest_lengths"].cpu(), out["nbest_scores"].cpu().double()
+            for j in range(1, 5):
+                lpj = o.sequence_logprob(xs, nt[rows, j], nl[rows, j])
+                expj = lpj / (nl[rows, j] - 1).double()
+                assert float(((ns[rows, j] - expj).abs() / expj.abs()).max()) < BF16_LOGIT_TOL, (j, ns[rows, j], expj)
+            # distinct hypotheses everywhere in the batch
+            for b in range(0, 1024, 37):
+                hs = {tuple(nt[b, j, : nl[b, j]].tolist()) for j in range(5) if nl[b, j] > 0}
+                assert len(hs) == int((nl[b] > 0).sum())
+
+
+def test_bf16_masked_encoder_and_decode_vs_oracle():
+    """bf16 mode with a ragged video_mask (pack_padded_sequence branch, encoder.py:74-82: per-timestep launches of
+    gemm_tc_direct_kernel with the length-aware LSTM epilogue): encoder outputs / final state and teacher-forced logits
+    + attention weights within the bf16 bar of the oracle; also at a batch large enough for the persistent GEMMs."""
+    from oracle import synth
+    for shape, B, lens in (("tiny", 4, [16, 9, 12, 5]), ("small", 300, None)):
+        cfg = synth.make_config(shape)
+        V, T, F = cfg.model.vocab_size, cfg.model.video_sequence_length, cfg.model.cnn_feature_dim
+        sd = synth.make_state_dict(cfg, V, "bahdanau", seed=51, logit_gain=4.0)
+        o = make_oracle(sd)
+        x = torch.from_numpy(synth.make_features(B, T, F, seed=52))
+        if lens is None:
+            lens = [T - (b * 5) % (T - 2) for b in range(B)]
+            lens[0] = T
+        mask = torch.ones(B, T)
+        for b, n in enumerate(lens):
+            mask[b, n:] = 0
+        sel = list(range(4)) if B == 4 else [0, 1, 7, 150, 299]
+        e_o, f_o = o.encode(x, mask)
+        m = make_native_model(cfg, V, sd, "bahdanau", "bf16")
+        e, f = m.encoder(x.cuda(), mask.cuda())
+        assert rel_err(e.cpu()[sel], e_o[sel]) < BF16_LOGIT_TOL and rel_err(f.cpu()[sel], f_o[sel]) < BF16_LOGIT_TOL
+        inp = torch.randint(4, V, (B, 6), generator=torch.Generator().manual_seed(3))
+        inp[:, 0] = START
+        tf_o = o.forward_teacher(x[sel], inp[sel], mask[sel])
+        tf = m(x.cuda(), inp.cuda(), None, video_mask=mask.cuda())
+        assert rel_err(tf["logits"].cpu()[sel], tf_o["logits"]) < BF16_LOGIT_TOL
+        assert np.abs(tf["attention_weights"].cpu().numpy()[sel] - tf_o["attention_weights"].numpy()).max() < 2e-2
+
+
+def test_config5_shape_vs_oracle():
+    """BASELINE configs[4] shape (V=30 000, max_len 30, beam 5, bf16) at B=96: teacher-forced logits of sampled rows
+    within 2e-2 of the oracle and beam scores against the oracle's log-probability of the GPU's tokens."""
+    from oracle import synth
+    cfg = synth.make_config("c5")
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, "bahdanau", seed=5, logit_gain=8.0, end_token_id=END, end_bias=0.5)
+    B, S = 96, 30
+    x = torch.from_numpy(synth.make_features(B, 80, 4096, seed=6, kind="ragged"))
+    rows = [0, 41, 95]
+    o = make_oracle(sd)
+    m = make_native_model(cfg, V, sd, "bahdanau", "bf16")
+    inp = torch.randint(4, V, (B, S), generator=torch.Generator().manual_seed(2))
+    inp[:, 0] = START
+    tf_o = o.forward_teacher(x[rows], inp[rows])
+    tf = m(x.cuda(), inp.cuda(), None)
+    assert rel_err(tf["logits"][rows].cpu(), tf_o["logits"]) < BF16_LOGIT_TOL
+    del tf
+    for diverse in (False, True):
+        out = m.generate(x.cuda(), START, END, max_length=S, method="beam", beam_size=5, diverse_beams=diverse)
+        t, l, sc = out["generated_tokens"].cpu(), out["lengths"].cpu(), out["scores"].cpu().double()
+        lpo = o.sequence_logprob(x[rows], t[rows], l[rows])
+        ll = l[rows]
+        ended = t[rows][torch.arange(len(rows)), ll - 1] == END
+        exp = torch.where(ended, lpo / (ll - 1).double(), lpo)
+        assert float(((sc[rows] - exp).abs() / exp.abs()).max()) < BF16_LOGIT_TOL, (diverse, sc[rows], exp)
+
+
+@pytest.mark.parametrize("att", ["luong_general", "luong_dot"])
+def test_config3_shape_large_batch_vs_oracle(att):
+    """BASELINE configs[2] shape (H=1024, Luong general / dot, 2-layer decoder, beam 5) at B=512, bf16: sampled rows'
+    encoder outputs and teacher-forced logits within 2e-2 of the oracle; beam scores vs the oracle's log-probability."""
+    from oracle import synth
+    cfg = synth.make_config("c3")
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, att, seed=61, logit_gain=8.0, end_token_id=END, end_bias=0.4)
+    B, S = 512, 10
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(B, 80, 4096, generator=g, device="cuda")
+    rows = [0, 300, 511]
+    xs = x[rows].cpu()
+    o = make_oracle(sd)
+    m = make_native_model(cfg, V, sd, att, "bf16")
+    inp = torch.randint(4, V, (B, S), generator=torch.Generator().manual_seed(2))
+    inp[:, 0] = START
+    tf_o = o.forward_teacher(xs, inp[rows])
+    tf = m(x, inp.cuda(), None)
+    assert rel_err(tf["encoder_outputs"][rows].cpu(), tf_o["encoder_outputs"]) < BF16_LOGIT_TOL
+    assert rel_err(tf["logits"][rows].cpu(), tf_o["logits"]) < BF16_LOGIT_TOL
+    del tf
+    out = m.generate(x, START, END, max_length=S, method="beam", beam_size=5, diverse_beams=True)
+    t, l, sc = out["generated_tokens"].cpu(), out["lengths"].cpu(), out["scores"].cpu().double()
+    lpo = o.sequence_logprob(xs, t[rows], l[rows])
+    ll = l[rows]
+    ended = t[rows][torch.arange(len(rows)), ll - 1] == END
+    exp = torch.where(ended, lpo / (ll - 1).double(), lpo)
+    assert float(((sc[rows] - exp).abs() / exp.abs()).max()) < BF16_LOGIT_TOL, (sc[rows], exp)
+
+
+# ------------------------------------------------------------------ round-1 advisor findings
+@pytest.mark.parametrize("V", [1001, 1003, 2502])
+def test_arbitrary_vocabulary_size(V):
+    """len(vocabulary) of a reference checkpoint is arbitrary: the vocabulary is padded internally to a multiple of 4
+    (zero weight rows, -1e30 bias); greedy / beam / diverse tokens, scores and teacher-forced logits [B,L,V] must equal
+    the oracle's exactly as for an aligned vocabulary, in both precisions."""
+    from oracle import synth
+    cfg = synth.make_config("tiny", V=V)
+    sd = synth.make_state_dict(cfg, V, "bahdanau", seed=V, logit_gain=4.0, end_token_id=END, end_bias=0.3)
+    feats = synth.make_features(5, 16, 256, seed=8, kind="ragged")
+    o = make_oracle(sd)
+    x = torch.from_numpy(feats).cuda()
+    gr = o.greedy(feats, START, END, max_length=10)
+    bm = o.beam(feats, START, END, max_length=10, beam_size=4, diverse=True, num_return=4)
+    inp = torch.cat([torch.full((5, 1), START), gr["generated_tokens"][:, :-1]], 1)
+    tf_o = o.forward_teacher(feats, inp)["logits"]
+    m = make_native_model(cfg, V, sd, "bahdanau", "fp32")
+    assert torch.equal(m.generate(x, START, END, max_length=10)["generated_tokens"].cpu(), gr["generated_tokens"])
+    out = m.generate(x, START, END, max_length=10, method="beam", beam_size=4, diverse_beams=True, num_return_sequences=4)
+    assert torch.equal(out["lengths"].cpu(), bm["lengths"])
+    assert torch.equal(out["generated_tokens"].cpu(), bm["generated_tokens"][:, : out["generated_tokens"].shape[1]])
+    assert torch.equal(out["nbest_lengths"].cpu(), bm["nbest_lengths"])
+    tf = m(x, inp.cuda(), None)["logits"]
+    assert tuple(tf.shape) == (5, inp.shape[1], V) and rel_err(tf.cpu(), tf_o) < FP32_LOGIT_TOL
+    m.set_precision("bf16")
+    tf = m(x, inp.cuda(), None)["logits"]
+    assert tuple(tf.shape) == (5, inp.shape[1], V) and rel_err(tf.cpu(), tf_o) < BF16_LOGIT_TOL
+    t = m.generate(x, START, END, max_length=10, method="beam", beam_size=4)["generated_tokens"]
+    assert int(t.max()) < V and int(t.min()) >= 0
+
+
+def test_token_ids_are_range_checked():
+    from oracle import synth
+    cfg = synth.make_config("tiny")
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, "bahdanau", seed=1)
+    m = make_native_model(cfg, V, sd, "bahdanau", "fp32")
+    x = torch.from_numpy(synth.make_features(2, 16, 256, seed=2)).cuda()
+    with pytest.raises(ValueError, match="start_token_id"):
+        m.generate(x, V + 5, END, max_length=4)
+    with pytest.raises(ValueError, match="start_token_id"):
+        m.generate(x, -1, END, max_length=4, method="beam", beam_size=2)
+    with pytest.raises(IndexError):
+        m(x, torch.tensor([[1, V], [1, 5]]).cuda(), None)
+    # an out-of-range END id means "never stop" (dead beam slots are fed a clamped token): must run and never emit it
+    t = m.generate(x, START, -1, max_length=5, method="beam", beam_size=3)
+    assert t["generated_tokens"].shape[1] == 6 and int(t["generated_tokens"].min()) >= 0
+    assert m.generate(x[:0], START, END, max_length=4, method="beam")["generated_tokens"].shape[0] == 0      # empty batch
+
+
+def test_host_packed_ingest_with_ragged_mask():
+    """bf16 host ingest with a pinned CPU video_mask spanning several windows / decode chunks (the mask copy used to be
+    enqueued on the copy stream after the chunk's ready event): results must equal the device-resident call."""
+    from oracle import synth
+    cfg = synth.make_config("tiny")
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, "bahdanau", seed=71, logit_gain=4.0, end_token_id=END, end_bias=0.3)
+    m = make_native_model(cfg, V, sd, "bahdanau", "bf16")
+    m.host_pack = True
+    m.host_window_size = 14
+    m.host_chunk_fractions = (0.3, 0.7, 1.0)
+    m.host_piece_size = 3
+    m.host_pack_threads = 2
+    B, T = 37, 16
+    host = torch.from_numpy(synth.make_features(B, T, 256, seed=72, kind="ragged")).pin_memory()
+    mask = torch.ones(B, T)
+    for b in range(B):
+        mask[b, T - (b * 5) % (T - 3):] = 0
+    mask = mask.pin_memory()
+    dev16 = host.cuda().to(torch.bfloat16)
+    for method, kw in (("greedy", {}), ("beam", {"beam_size": 3})):
+        a = m.generate(dev16, START, END, max_length=9, method=method, video_mask=mask.cuda(), **kw)
+        for _ in range(3):
+            b_ = m.generate(host, START, END, max_length=9, method=method, video_mask=mask, **kw)
+            assert torch.equal(a["generated_tokens"], b_["generated_tokens"])

@@ -178,3 +178,72 @@ def test_host_pack_auto_depends_on_ranks_per_node(monkeypatch):
     assert vc.VideoCaptioningModel(cfg, 1000, precision="bf16").host_pack is True
     monkeypatch.setenv("VC_HOST_PACK", "0")
     assert vc.VideoCaptioningModel(cfg, 1000, precision="bf16").host_pack is False
+
+
+class _FakeModel:
+    """Stands in for VideoCaptioningModel in the sharding test (no GPU here): row i's tokens encode its video id."""
+
+    def generate(self, video_features, start_token_id, end_token_id, max_length=20, video_mask=None, method="greedy", **kw):
+        n = video_features.shape[0]
+        if n == 0:
+            return {"generated_tokens": torch.zeros(0, 1, dtype=torch.int64), "lengths": torch.zeros(0, dtype=torch.int64),
+                    "scores": torch.zeros(0)}
+        ids = video_features[:, 0, 0].to(torch.int64)
+        toks = torch.stack([torch.full((n,), start_token_id), ids + 10, torch.full((n,), end_token_id)], dim=1)
+        return {"generated_tokens": toks, "lengths": torch.full((n,), 3, dtype=torch.int64), "scores": torch.zeros(n)}
+
+
+def _empty_shard_worker(rank, world, port, q):
+    from video_captioning_b200.sharding import ShardedCaptioner
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = torch.arange(1, dtype=torch.float32).view(1, 1, 1).expand(1, 2, 4).clone()      # ONE video, two ranks
+    out = ShardedCaptioner(_FakeModel()).generate(x, 1, 2, max_length=5, method="beam", already_sharded=False, beam_size=3)
+    q.put((rank, out["generated_tokens"].tolist(), out["lengths"].tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharded_captioner_empty_shard_gloo_world2():
+    """Fewer videos than ranks: the rank with the empty shard must still take part in the gather."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_empty_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+    for _, t, l in res:
+        assert t == [[1, 10, 2]] and l == [3]
+
+
+def test_model_dimension_limits_raise_at_construction():
+    """Arbitrary vocabulary sizes are accepted (len(vocabulary) of a reference checkpoint is arbitrary); unsupported
+    F/H/E/A raise a ValueError when the model is built, not at the first generate()."""
+    cfg = synth.make_config("tiny")
+    vc.VideoCaptioningModel(cfg, 1003)                      # odd vocabulary: fine
+    vc.VideoCaptioningModel(cfg, 1003, precision="bf16")
+    bad = synth.make_config("tiny", E=100)
+    with pytest.raises(ValueError):
+        vc.VideoCaptioningModel(bad, 1000)
+    bad = synth.make_config("tiny", H=136)                  # multiple of 8, not of 64
+    vc.VideoCaptioningModel(bad, 1000)
+    with pytest.raises(ValueError):
+        vc.VideoCaptioningModel(bad, 1000, precision="bf16")
+    with pytest.raises(ValueError):
+        vc.VideoCaptioningModel(bad, 1000).set_precision("bf16")
+    with pytest.raises(ValueError):
+        vc.VideoCaptioningModel(cfg, 3)
+
+
+def test_library_staleness_is_detected_by_source_hash(tmp_path, monkeypatch):
+    """A libvc_b200.so built from other sources than the tree's must not be loaded silently."""
+    from video_captioning_b200 import _native
+    assert _native.library_is_current()                     # conftest / build() left a current library
+    monkeypatch.setattr(_native, "_HASH_PATH", str(tmp_path / "h"))
+    assert not _native.library_is_current()                 # no hash file: treated as stale
+    (tmp_path / "h").write_text("0" * 64)
+    assert not _native.library_is_current()
+    (tmp_path / "h").write_text(_native.sources_hash())
+    assert _native.library_is_current()

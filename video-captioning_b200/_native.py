@@ -7,7 +7,10 @@ returns a non-zero status, a ``RuntimeError`` is raised.  PyTorch is used here o
 from __future__ import annotations
 
 import ctypes
+import hashlib
+import logging
 import os
+import shutil
 import subprocess
 import threading
 from typing import Dict, Optional
@@ -34,7 +37,7 @@ PRECISION_IDS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 EXPORTED_SYMBOLS = (
     "vc_last_error", "vc_version", "vc_launch_count", "vc_profile_begin", "vc_profile_end", "vc_model_create", "vc_model_set_weight", "vc_model_finalize",
     "vc_model_destroy", "vc_workspace_bytes", "vc_encoder_forward", "vc_attn_precompute",
-    "vc_decode_greedy", "vc_decode_beam", "vc_generate", "vc_generate_ex", "vc_host_pack_bf16", "vc_convert_bf16",
+    "vc_decode_greedy", "vc_decode_beam", "vc_beam_nbest", "vc_generate", "vc_generate_ex", "vc_host_pack_bf16", "vc_convert_bf16",
     "vc_forward_teacher", "vc_linear",
     "vc_attention_step", "vc_beam_select",
 )
@@ -59,20 +62,42 @@ def nvcc_command(out_path: str = LIB_PATH):
             os.path.join(_CSRC, "host_pack.cpp")]
 
 
-def _sources_mtime() -> float:
-    files = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [os.path.join(_INCLUDE, "vc_b200.h")]
-    return max(os.path.getmtime(f) for f in files)
+def _source_files():
+    return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC)) + [os.path.join(_INCLUDE, "vc_b200.h")]
+
+
+def sources_hash() -> str:
+    """Hash of everything the library is compiled from (mtimes do not survive a copy of the tree)."""
+    h = hashlib.sha256()
+    for f in _source_files():
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+_HASH_PATH = LIB_PATH + ".srchash"
+
+
+def library_is_current() -> bool:
+    if not (os.path.exists(LIB_PATH) and os.path.exists(_HASH_PATH)):
+        return False
+    with open(_HASH_PATH) as fh:
+        return fh.read().strip() == sources_hash()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/capi.cu for sm_100a into libvc_b200.so (in-tree).  Cross-compiles without a GPU."""
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _sources_mtime():
+    """Compile csrc/capi.cu for sm_100a into libvc_b200.so (in-tree).  Cross-compiles without a GPU.  The hash of the
+    sources is stored beside the library, so a library left over from older sources is never loaded silently."""
+    if not force and library_is_current():
         return LIB_PATH
     cmd = nvcc_command(LIB_PATH + ".tmp")
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed building libvc_b200.so:\n" + proc.stdout + proc.stderr)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    with open(_HASH_PATH, "w") as fh:
+        fh.write(sources_hash())
     if verbose:
         print(proc.stdout + proc.stderr)
     return LIB_PATH
@@ -88,7 +113,11 @@ def load_library() -> ctypes.CDLL:
     with _lib_lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        if not library_is_current():
+            # missing, or compiled from other sources than the ones in the tree (an edited csrc/ or header): rebuild
+            if shutil.which("nvcc") is None:
+                raise RuntimeError(f"{LIB_PATH} is missing or stale (csrc/ changed since it was built) and nvcc is not on "
+                                   "PATH to rebuild it; there is no fallback path")
             build_library()
         lib = ctypes.CDLL(LIB_PATH)
         vp, i32, i64, f32p, i32p = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p
@@ -111,6 +140,7 @@ def load_library() -> ctypes.CDLL:
         lib.vc_attn_precompute.argtypes = [vp, i32, i32, vp, sz, vp]
         lib.vc_decode_greedy.argtypes = [vp, i32, i32, f32p, ctypes.POINTER(DecodeParams), i32p, f32p, vp, sz, vp]
         lib.vc_decode_beam.argtypes = [vp, i32, i32, f32p, ctypes.POINTER(DecodeParams), i32p, i32p, f32p, vp, sz, vp]
+        lib.vc_beam_nbest.argtypes = [vp, i32, i32, ctypes.POINTER(DecodeParams), i32, i32p, i32p, f32p, vp, sz, vp]
         lib.vc_generate.argtypes = [vp, f32p, i32, i32, i32p, f32p, ctypes.POINTER(DecodeParams), i32p, i32p, f32p,
                                     f32p, vp, sz, vp]
         lib.vc_generate_ex.argtypes = [vp, vp, i32, i32, i32, i32p, f32p, ctypes.POINTER(DecodeParams), i32p, i32p, f32p,
@@ -275,7 +305,9 @@ class NativeModel:
         return enc_out, final
 
     def generate(self, feats, start, end, max_length, mask=None, method="greedy", beam_size=5, length_penalty=1.0,
-                 temperature=1.0, diverse=False, want_attention=True):
+                 temperature=1.0, diverse=False, want_attention=True, nbest=0):
+        """-> (tokens, lengths, scores, attention[, nbest_tokens [B,N,S+1], nbest_lengths [B,N], nbest_scores [B,N]]);
+        the n-best triple (vc_beam_nbest) is appended when ``nbest`` > 0 (beam only)."""
         f = self._prep_feats(feats, allow_bf16=self.desc.precision == PREC_BF16)
         dtype_id = 1 if f.dtype == torch.bfloat16 else 0
         B, T, _ = f.shape
@@ -284,18 +316,27 @@ class NativeModel:
         beam = method == "beam"
         K = int(beam_size) if beam else 1
         p = self._params(method, K, S, start, end, length_penalty, temperature, diverse)
+        N = int(nbest) if beam else 0
 
         def alloc():
-            return (torch.empty(B, S + 1 if beam else S, dtype=torch.int32, device=self.device),
+            base = (torch.empty(B, S + 1 if beam else S, dtype=torch.int32, device=self.device),
                     torch.empty(B, dtype=torch.int32, device=self.device) if beam else None,
                     torch.empty(B, dtype=torch.float32, device=self.device) if beam else None,
                     torch.empty(B, S, T, dtype=torch.float32, device=self.device) if (want_attention and not beam) else None)
+            if N > 0:
+                base += (torch.empty(B, N, S + 1, dtype=torch.int32, device=self.device),
+                         torch.empty(B, N, dtype=torch.int32, device=self.device),
+                         torch.empty(B, N, dtype=torch.float32, device=self.device))
+            return base
 
         def launch(outs, ws):
-            tokens, lens, scores, attn = outs
+            tokens, lens, scores, attn = outs[:4]
             check(self.lib.vc_generate_ex(self._h, _ptr(f), dtype_id, B, T, _ptr(lengths), _ptr(m), ctypes.byref(p),
                                           _ptr(tokens), _ptr(lens), _ptr(scores), _ptr(attn), _ptr(ws), ws.numel(),
                                           _stream(self.device)), "vc_generate")
+            if N > 0:
+                check(self.lib.vc_beam_nbest(self._h, B, T, ctypes.byref(p), N, _ptr(outs[4]), _ptr(outs[5]), _ptr(outs[6]),
+                                             _ptr(ws), ws.numel(), _stream(self.device)), "vc_beam_nbest")
 
         with torch.cuda.device(self.device):
             ws = self._workspace(B, T, K, S)
@@ -305,7 +346,7 @@ class NativeModel:
             key = None
             if self._graphs_on and not _profiling and m is None and f.data_ptr() == feats.data_ptr():
                 key = (f.data_ptr(), dtype_id, B, T, K, S, method, int(start), int(end), float(length_penalty),
-                       float(temperature), bool(diverse), bool(want_attention), ws.data_ptr(), ws.numel())
+                       float(temperature), bool(diverse), bool(want_attention), N, ws.data_ptr(), ws.numel())
             ent = self._graphs.get(key) if key is not None else None
             global _replayed_launches
             if ent is not None:
@@ -330,8 +371,12 @@ class NativeModel:
                         self._graphs[key] = (g, outs, f, ws, n_launch)     # keeps the captured buffers alive
                         g.replay()
                         return tuple(None if t is None else t.clone() for t in outs)
-                    except Exception:
-                        # capture not possible here (e.g. a launch attribute the driver cannot record): plain launches
+                    except RuntimeError as e:
+                        # stream capture failed (torch raises RuntimeError / its subclass AcceleratorError for a launch the
+                        # driver cannot record, and for a non-zero status of the library inside the capture): say so once and
+                        # keep this handle on plain launches.  Anything else (ValueError of a bad argument, ...) propagates.
+                        logging.getLogger(__name__).warning("CUDA-graph capture of generate() failed, using plain launches "
+                                                            "for this handle: %s", e)
                         self._graphs_on = False
                         self._graphs.clear()
                         torch.cuda.synchronize(self.device)
@@ -345,6 +390,8 @@ class NativeModel:
         m, lengths = self._prep_mask(mask, B, T, self.device)
         tok = input_tokens.detach().to(device=self.device, dtype=torch.int32).contiguous()
         L = tok.shape[1]
+        if tok.numel() and (int(tok.min()) < 0 or int(tok.max()) >= self.V):
+            raise IndexError(f"input_tokens outside the vocabulary [0, {self.V})")     # nn.Embedding raises too (decoder.py:130)
         logits = torch.empty(B, L, self.V, dtype=torch.float32, device=self.device)
         attn = torch.empty(B, L, T, dtype=torch.float32, device=self.device) if want_attention else None
         enc_out = torch.empty(B, T, self.H, dtype=torch.float32, device=self.device)

@@ -10,7 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -37,9 +39,12 @@ void set_error(const char* fmt, ...) {
 // Every kernel launch of the path goes through a LaunchScope: it counts launches (bench.py's
 // `gpu_launches`) and, when profiling is enabled (vc_profile_begin), brackets the launch with CUDA events
 // recorded on the launching stream so bench.py can attribute device time to kernel classes.
+// Process-global (it serves bench.py, one measuring thread); handles may still be driven from several threads: the counter
+// is atomic and the event bookkeeping is serialised by a mutex.
 struct Profiler {
-  bool on = false;
-  long long launches = 0;
+  std::atomic<bool> on{false};
+  std::atomic<long long> launches{0};
+  std::mutex mu;
   std::vector<cudaEvent_t> pool;
   size_t used = 0;
   struct Rec { int cls; cudaEvent_t a, b; };
@@ -59,8 +64,9 @@ struct LaunchScope {
   cudaStream_t s;
   cudaEvent_t b = nullptr;
   LaunchScope(int cls, cudaStream_t stream, int n = 1) : s(stream) {
-    g_prof.launches += n;
-    if (g_prof.on) {
+    g_prof.launches.fetch_add(n, std::memory_order_relaxed);
+    if (g_prof.on.load(std::memory_order_relaxed)) {
+      std::lock_guard<std::mutex> lock(g_prof.mu);
       cudaEvent_t a = g_prof.get();
       b = g_prof.get();
       cudaEventRecord(a, s);
@@ -113,6 +119,7 @@ struct vc_model {
   std::vector<void*> owned;
   bool finalized = false;
   int num_sms = 148;
+  int Vp = 0;                             // vocabulary size padded to a multiple of 4 (float4 / TMA row alignment): pad rows of the embedding and W_v are 0, pad biases -1e30, so a pad column never wins a max and adds 0 to a sum of exponentials
   bool disable_persistent_lstm = false;   // VC_DISABLE_PERSISTENT_LSTM=1: per-timestep launches (A/B testing)
   bool disable_tf32_proj = false;         // VC_DISABLE_TF32_PROJ=1: convert the features to bf16 first (A/B testing)
   int dbg_vocab = 0;                      // VC_DEBUG_VOCAB: timing experiments (gemm_tc.cuh VocabStats::dbg), results invalid
@@ -242,7 +249,18 @@ int finalize_model(vc_model* m, cudaStream_t s) {
   VC_TRY(plain("encoder.output_projection.weight", H, 2 * H, &m->Wo));
   VC_TRY(biasv("encoder.output_projection.bias", H, &m->bo));
   // decoder (decoder.py:33-59)
-  VC_TRY(plain("decoder.embedding.weight", V, E, &m->emb));
+  const int Vp = m->Vp;
+  auto padded_rows = [&](const std::string& key, int cols, void** dst) -> int {     // [V, cols] -> [Vp, cols], pad rows zero
+    const float* p;
+    VC_TRY(get_raw(m, key, (int64_t)V * cols, &p));
+    W* w;
+    VC_TRY(dev_alloc(m, &w, (size_t)Vp * cols));
+    if (Vp > V) VC_CUDA(cudaMemsetAsync(w + (size_t)V * cols, 0, sizeof(W) * (size_t)(Vp - V) * cols, s));
+    VC_TRY(prep_block<W>(s, w, cols, 0, p, cols, 0, V, cols, 0));
+    *dst = w;
+    return VC_OK;
+  };
+  VC_TRY(padded_rows("decoder.embedding.weight", E, &m->emb));
   switch (d.attention) {
     case VC_ATTN_BAHDANAU: {
       VC_TRY(plain("decoder.attention.encoder_projection.weight", A, H, &m->Wkey));
@@ -313,8 +331,17 @@ int finalize_model(vc_model* m, cudaStream_t s) {
     m->Wc = w;
     VC_TRY(biasv("decoder.context_projection.bias", H, &m->bc));
   }
-  VC_TRY(plain("decoder.output_projection.weight", V, H, &m->Wv));
-  VC_TRY(biasv("decoder.output_projection.bias", V, &m->bv));
+  VC_TRY(padded_rows("decoder.output_projection.weight", H, &m->Wv));
+  {
+    const float* p;
+    VC_TRY(get_raw(m, "decoder.output_projection.bias", V, &p));
+    VC_TRY(dev_alloc(m, &m->bv, (size_t)Vp));
+    if (Vp > V) {
+      const float pad[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
+      VC_CUDA(cudaMemcpyAsync(m->bv + V, pad, sizeof(float) * (size_t)(Vp - V), cudaMemcpyHostToDevice, s));
+    }
+    VC_TRY(prep_bias(s, m->bv, p, nullptr, V, 0));
+  }
   VC_CUDA(cudaStreamSynchronize(s));
   m->finalized = true;
   return VC_OK;
@@ -345,7 +372,7 @@ struct WS {
   float2* vs_part;       // [R, np] log-sum-exp partials
   unsigned int* dec_sync; // [dec_layers][ceil(R/128)] tile-level hand-over counters between stacked decoder LSTM GEMMs
   int* vs_rowthr;        // [R] shared pruning threshold of a row (ordered-int key of a float), reset by the selection kernel
-  int *cand_idx, *parent, *cur_tok, *done, *best_len, *best_seq, *hist[2];
+  int *cand_idx, *parent, *cur_tok, *done, *best_len, *best_slot, *best_seq, *hist[2];
   unsigned char* alive;
   size_t total;
 };
@@ -355,7 +382,7 @@ WS<ActT> carve(const vc_model_desc_t& d, void* base, int B, int T, int K, int S)
   WS<ActT> w;
   memset(&w, 0, sizeof(w));
   Carver c(base);
-  const size_t F = d.feature_dim, H = d.hidden_dim, E = d.embed_dim, A = d.attn_dim, V = d.vocab_size;
+  const size_t F = d.feature_dim, H = d.hidden_dim, E = d.embed_dim, A = d.attn_dim, V = align_up((size_t)d.vocab_size, 4);   // vc_model::Vp
   const size_t BT = (size_t)B * T, R = (size_t)B * K;
   if (!std::is_same<ActT, float>::value) w.feats_bf16 = c.take<bf16>(BT * F);
   w.proj = c.take<ActT>(BT * H);
@@ -396,9 +423,10 @@ WS<ActT> carve(const vc_model_desc_t& d, void* base, int B, int T, int K, int S)
   w.scores = c.take<float>(R);
   w.alive = c.take<unsigned char>(R);
   w.done = c.take<int>(B);
-  w.best_score = c.take<float>(B);
-  w.best_len = c.take<int>(B);
-  w.best_seq = c.take<int>((size_t)B * S);
+  w.best_score = c.take<float>(R);          // finished-hypothesis pool: K entries per video (decode.cuh BeamState)
+  w.best_len = c.take<int>(R);
+  w.best_slot = c.take<int>(R);
+  w.best_seq = c.take<int>(R * S);
   w.hist[0] = c.take<int>(R * S);
   w.hist[1] = c.take<int>(R * S);
   w.total = align_up(c.off, 256);
@@ -720,7 +748,8 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
                const int* teacher_tokens, float* teacher_logits, cudaStream_t s) {
   constexpr bool P = std::is_same<ActT, float>::value;
   const vc_model_desc_t& d = m->d;
-  const int H = d.hidden_dim, E = d.embed_dim, V = d.vocab_size, L = d.dec_layers;
+  const int H = d.hidden_dim, E = d.embed_dim, V = m->Vp, L = d.dec_layers;     // V: padded vocabulary (pad columns are inert)
+  const int Vu = d.vocab_size;                 // columns of the caller's teacher-forced logits
   const int R = B * K;
   const int64_t ZW = E + 3 * H;
 
@@ -735,7 +764,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
 
   BeamState bs;
   bs.scores = w.scores; bs.alive = w.alive; bs.done = w.done; bs.best_score = w.best_score; bs.best_len = w.best_len;
-  bs.best_seq = w.best_seq; bs.hist[0] = w.hist[0]; bs.hist[1] = w.hist[1];
+  bs.best_slot = w.best_slot; bs.best_seq = w.best_seq; bs.hist[0] = w.hist[0]; bs.hist[1] = w.hist[1];
 
   VC_CUDA(cudaMemsetAsync(w.flags + 512, 0, sizeof(unsigned int) * 512, s));   // attention scoring-gate counters (per SM)
   if (w.vs_rowthr != nullptr) VC_CUDA(cudaMemsetAsync(w.vs_rowthr, 0x80, sizeof(int) * (size_t)R, s));   // key of a very negative float
@@ -749,9 +778,9 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
   }
   {
     VC_SCOPE(VC_CLS_MISC);
-    decode_init_kernel<ActT><<<R, 128, 0, s>>>(st, w.final_f32, R, K, p.start_token_id,
+    decode_init_kernel<ActT><<<R, 128, 0, s>>>(st, w.final_f32, R, K, p.start_token_id, V,
                                              mode == DM_TEACHER ? teacher_tokens : nullptr, (int64_t)S, w.cur_tok, w.scores,
-                                               w.alive, w.done, w.best_score, w.best_len, p.diverse_beams);
+                                               w.alive, w.done, w.best_score, w.best_len, w.best_slot, p.diverse_beams);
   }
   VC_CUDA(cudaGetLastError());
 
@@ -861,8 +890,11 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       VC_TRY((gemm<ActT>(g, ZW, estore<ActT, true, P>(w.O, H, m->bc), s)));
     }
     // vocabulary projection (:169)
-    float* lg = (mode == DM_TEACHER) ? teacher_logits + (size_t)step * V : w.logits;
-    const int64_t ldl = (mode == DM_TEACHER) ? (int64_t)S * V : V;
+    // teacher forcing writes the caller's [B,S,V] logits directly when the rows are 16-byte aligned (V % 4 == 0), else
+    // through the padded workspace rows + a strided copy
+    const bool tf_direct = mode == DM_TEACHER && Vu == V;
+    float* lg = tf_direct ? teacher_logits + (size_t)step * V : w.logits;
+    const int64_t ldl = tf_direct ? (int64_t)S * V : V;
     const int vtn = (V + 255) / 256;
     // bf16 mode: the GEMM epilogue also emits per-row chunk maxima + log-sum-exp partials, and the selection
     // reads those instead of the whole logits row (decode.cuh: select_fused_kernel)
@@ -885,6 +917,11 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       } else {
         VC_TRY((gemm<ActT>(gargs(w.O, H, m->Wv, H, R, V, H), H, estore<float, false, P>(lg, ldl, m->bv), s)));
       }
+    }
+    if (mode == DM_TEACHER && !tf_direct) {
+      VC_SCOPE(VC_CLS_MISC);
+      VC_CUDA(cudaMemcpy2DAsync(teacher_logits + (size_t)step * Vu, sizeof(float) * (size_t)S * Vu, w.logits, sizeof(float) * (size_t)V,
+                                sizeof(float) * (size_t)Vu, (size_t)R, cudaMemcpyDeviceToDevice, s));
     }
     // selection
     const int* parent = nullptr;
@@ -970,9 +1007,10 @@ extern "C" {
 const char* vc_last_error(void) { return g_err; }
 int vc_version(void) { return 100; }
 
-long long vc_launch_count(void) { return g_prof.launches; }
+long long vc_launch_count(void) { return g_prof.launches.load(std::memory_order_relaxed); }
 
 int vc_profile_begin(void) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   g_prof.on = true;
   g_prof.used = 0;
   g_prof.recs.clear();
@@ -983,6 +1021,7 @@ int vc_profile_end(float* ms_per_class, int32_t* launches_per_class) {
   VC_CHECK(ms_per_class != nullptr && launches_per_class != nullptr, "null argument");
   g_prof.on = false;
   VC_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   for (int c = 0; c < VC_CLS_COUNT; ++c) { ms_per_class[c] = 0.f; launches_per_class[c] = 0; }
   for (const auto& r : g_prof.recs) {
     float ms = 0.f;
@@ -998,10 +1037,10 @@ int vc_profile_end(float* ms_per_class, int32_t* launches_per_class) {
 int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   VC_CHECK(desc != nullptr && out != nullptr, "null argument");
   const vc_model_desc_t& d = *desc;
-  VC_CHECK(d.hidden_dim > 0 && d.hidden_dim % 8 == 0 && d.feature_dim % 8 == 0 && d.embed_dim % 8 == 0 &&
-               d.attn_dim % 8 == 0 && d.vocab_size % 4 == 0,
-           "dims must be multiples of 8 (vocab of 4): F=%d H=%d E=%d A=%d V=%d", d.feature_dim, d.hidden_dim, d.embed_dim,
-           d.attn_dim, d.vocab_size);
+  VC_CHECK(d.hidden_dim > 0 && d.hidden_dim % 8 == 0 && d.feature_dim > 0 && d.feature_dim % 8 == 0 && d.embed_dim > 0 &&
+               d.embed_dim % 8 == 0 && d.attn_dim > 0 && d.attn_dim % 8 == 0 && d.vocab_size >= 4,
+           "F, H, E, A must be positive multiples of 8 and the vocabulary >= 4 (any size: it is padded internally): "
+           "F=%d H=%d E=%d A=%d V=%d", d.feature_dim, d.hidden_dim, d.embed_dim, d.attn_dim, d.vocab_size);
   VC_CHECK(d.enc_layers >= 1 && d.enc_layers <= 4 && d.dec_layers >= 1 && d.dec_layers <= 4, "1..4 LSTM layers supported");
   VC_CHECK(d.precision == VC_PREC_FP32 || d.precision == VC_PREC_BF16, "unknown precision %d", d.precision);
   if (d.precision == VC_PREC_BF16)
@@ -1014,6 +1053,7 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   vc_model* m = new (std::nothrow) vc_model();
   VC_CHECK(m != nullptr, "out of host memory");
   m->d = d;
+  m->Vp = (d.vocab_size + 3) / 4 * 4;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
     m->num_sms = sms;
@@ -1137,6 +1177,8 @@ int vc_decode_greedy(vc_model_t* m, int32_t B, int32_t T, const float* mask, con
   const int S = p->max_length;
   VC_TRY(check_common(m, B, T, 1, S, ws_bytes, ws));
   VC_CHECK(p->temperature > 0.f, "temperature must be positive");
+  VC_CHECK(p->start_token_id >= 0 && p->start_token_id < m->d.vocab_size, "start_token_id %d outside the vocabulary [0, %d)",
+           p->start_token_id, m->d.vocab_size);
   if (m->d.precision == VC_PREC_FP32) {
     WS<float> w = carve<float>(m->d, ws, B, T, 1, S);
     return run_decode<float>(m, w, B, T, 1, S, mask, *p, DM_GREEDY, tokens, nullptr, nullptr, attn, nullptr, nullptr, s);
@@ -1151,12 +1193,38 @@ int vc_decode_beam(vc_model_t* m, int32_t B, int32_t T, const float* mask, const
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int S = p->max_length, K = p->beam_size;
   VC_TRY(check_common(m, B, T, K, S, ws_bytes, ws));
+  VC_CHECK(p->start_token_id >= 0 && p->start_token_id < m->d.vocab_size, "start_token_id %d outside the vocabulary [0, %d)",
+           p->start_token_id, m->d.vocab_size);
   if (m->d.precision == VC_PREC_FP32) {
     WS<float> w = carve<float>(m->d, ws, B, T, K, S);
     return run_decode<float>(m, w, B, T, K, S, mask, *p, DM_BEAM, tokens, lengths, scores, nullptr, nullptr, nullptr, s);
   }
   WS<bf16> w = carve<bf16>(m->d, ws, B, T, K, S);
   return run_decode<bf16>(m, w, B, T, K, S, mask, *p, DM_BEAM, tokens, lengths, scores, nullptr, nullptr, nullptr, s);
+}
+
+// n-best hypotheses of the beam decode that just ran in `ws` (same B, T, beam size and max_length)
+int vc_beam_nbest(vc_model_t* m, int32_t B, int32_t T, const vc_decode_params_t* p, int32_t N, int32_t* tokens, int32_t* lengths,
+                  float* scores, void* ws, size_t ws_bytes, vc_stream_t stream) {
+  VC_CHECK(p != nullptr && tokens != nullptr && lengths != nullptr && scores != nullptr, "null argument");
+  VC_CHECK(p->method == VC_METHOD_BEAM && N >= 1 && N <= 2 * p->beam_size, "vc_beam_nbest: beam decode and 1 <= N <= 2*beam_size expected");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int S = p->max_length, K = p->beam_size;
+  VC_TRY(check_common(m, B, T, K, S, ws_bytes, ws));
+  BeamState bs;
+  if (m->d.precision == VC_PREC_FP32) {
+    WS<float> w = carve<float>(m->d, ws, B, T, K, S);
+    bs.scores = w.scores; bs.alive = w.alive; bs.done = w.done; bs.best_score = w.best_score; bs.best_len = w.best_len;
+    bs.best_slot = w.best_slot; bs.best_seq = w.best_seq; bs.hist[0] = w.hist[0]; bs.hist[1] = w.hist[1];
+  } else {
+    WS<bf16> w = carve<bf16>(m->d, ws, B, T, K, S);
+    bs.scores = w.scores; bs.alive = w.alive; bs.done = w.done; bs.best_score = w.best_score; bs.best_len = w.best_len;
+    bs.best_slot = w.best_slot; bs.best_seq = w.best_seq; bs.hist[0] = w.hist[0]; bs.hist[1] = w.hist[1];
+  }
+  VC_SCOPE(VC_CLS_MISC);
+  beam_nbest_kernel<<<(B * N + 127) / 128, 128, 0, s>>>(bs, B, K, S, S, N, p->start_token_id, p->length_penalty, tokens, lengths, scores);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
 }
 
 // NOTE on workspace layout: the encoder-side buffers precede the decode-side ones and their sizes do not
@@ -1248,9 +1316,10 @@ int vc_beam_select(const float* logits, const float* scores, int32_t B, int32_t 
   bs.scores = c.take<float>(R);
   bs.alive = c.take<unsigned char>(R);
   bs.done = c.take<int>(B);
-  bs.best_score = c.take<float>(B);
-  bs.best_len = c.take<int>(B);
-  bs.best_seq = c.take<int>(B);
+  bs.best_score = c.take<float>(R);
+  bs.best_len = c.take<int>(R);
+  bs.best_slot = c.take<int>(R);
+  bs.best_seq = c.take<int>(R);
   bs.hist[0] = c.take<int>(R);
   bs.hist[1] = c.take<int>(R);
   if (ws == nullptr || ws_bytes < c.off) {
@@ -1259,7 +1328,8 @@ int vc_beam_select(const float* logits, const float* scores, int32_t B, int32_t 
   }
   VC_CUDA(cudaMemcpyAsync(bs.scores, scores, sizeof(float) * R, cudaMemcpyDeviceToDevice, s));
   VC_CUDA(cudaMemsetAsync(bs.alive, 1, R, s));
-  VC_CUDA(cudaMemsetAsync(bs.best_len, 0, sizeof(int) * B, s));
+  VC_CUDA(cudaMemsetAsync(bs.best_len, 0, sizeof(int) * R, s));
+  VC_CUDA(cudaMemsetAsync(bs.best_slot, 0, sizeof(int) * R, s));
   beam_row_topk_kernel<true><<<(int)R, 256, 0, s>>>(logits, V, V, K, cand_val, cand_idx);
   beam_select_kernel<<<(B + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, s>>>(bs, cand_val, cand_idx, B, K, V, 1, 0, /*end_id=*/-1, 1.0f, parent, token);
   VC_CUDA(cudaGetLastError());

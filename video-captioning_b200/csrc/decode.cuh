@@ -35,10 +35,11 @@ struct DecState {
 // ---------------------------------------------------------------- init (step -1)
 template <class ActT>
 __global__ void decode_init_kernel(DecState<ActT> st, const float* __restrict__ enc_final /*[B,H]*/, int R, int K,
-                                   int start_id, const int* __restrict__ init_tok, int64_t init_stride,
+                                   int start_id, int V, const int* __restrict__ init_tok, int64_t init_stride,
                                    int* __restrict__ cur_tok, float* __restrict__ scores,
                                    unsigned char* __restrict__ alive, int* __restrict__ done,
-                                   float* __restrict__ best_score, int* __restrict__ best_len, int diverse) {
+                                   float* __restrict__ best_score, int* __restrict__ best_len, int* __restrict__ best_slot,
+                                   int diverse) {
   const int r = blockIdx.x;
   const int b = r / K;
   for (int l = 0; l < st.L; ++l) {
@@ -47,7 +48,8 @@ __global__ void decode_init_kernel(DecState<ActT> st, const float* __restrict__ 
       st.c[l][(int64_t)r * st.H + u] = 0.f;                                                            // :104
     }
   }
-  const int tok0 = init_tok ? init_tok[(int64_t)r * init_stride] : start_id;   // teacher forcing feeds its own first token
+  int tok0 = init_tok ? init_tok[(int64_t)r * init_stride] : start_id;   // teacher forcing feeds its own first token
+  tok0 = min(max(tok0, 0), V - 1);     // ids are range-checked on the host (nn.Embedding would raise); never read out of bounds
   for (int e = threadIdx.x; e < st.E; e += blockDim.x)
     st.emb_dst[(int64_t)r * st.emb_ld + e] = st.emb_table[(int64_t)tok0 * st.E + e];
   if (threadIdx.x == 0) {
@@ -56,11 +58,11 @@ __global__ void decode_init_kernel(DecState<ActT> st, const float* __restrict__ 
     // standard beam search (only beam 0 live at step 0), SURVEY.md section 8f rank 3.
     if (scores) scores[r] = (diverse && (r % K) != 0) ? -INFINITY : 0.f;
     if (alive) alive[r] = 1;
-    if (r % K == 0) {
-      if (done) done[b] = 0;
-      if (best_score) best_score[b] = -INFINITY;
-      if (best_len) best_len[b] = 0;
-    }
+    if (r % K == 0 && done) done[b] = 0;
+    // finished-hypothesis pool of the video: K entries, row r = b*K + k owns entry k (empty: len 0)
+    if (best_score) best_score[r] = -INFINITY;
+    if (best_len) best_len[r] = 0;
+    if (best_slot) best_slot[r] = r % K;
   }
 }
 
@@ -330,9 +332,13 @@ struct BeamState {
   float* scores;            // [R]
   unsigned char* alive;     // [R]
   int* done;                // [B]
-  float* best_score;        // [B] best completed (normalised) score
-  int* best_len;            // [B] generated length of the best completed hypothesis (0 = none)
-  int* best_seq;            // [B,S]
+  // Finished-hypothesis pool, K entries per video, kept sorted by normalised score (descending; among equal scores the
+  // hypothesis completed first stays ahead -- the one `max` keeps at video_captioning_model.py:277-281).  Entry 0 is what
+  // the reference returns; the whole pool is the n-best list of the opt-in real beam search (vc_beam_nbest).
+  float* best_score;        // [B,K] normalised score
+  int* best_len;            // [B,K] generated length (0 = empty entry)
+  int* best_slot;           // [B,K] which of the video's K sequence slots holds the entry's tokens
+  int* best_seq;            // [B,K,S] sequence slots
   int* hist[2];             // [R,S] token history, ping-pong
 };
 
@@ -343,6 +349,7 @@ struct SelScratch {
   float v[16], ns[16];
   int pk[16], nt[16];     // selection order: parent beam, token
   int np[16], tk[16];     // compacted live beams: parent beam, token
+  int jslot[16], jpk[16]; // hypotheses completed this step that entered the pool: sequence slot, parent beam
   int misc[4];
 };
 
@@ -398,15 +405,26 @@ __device__ __forceinline__ void beam_select_video(const BeamState& bs, const flo
   __syncwarp();
   // END bookkeeping + compaction of the live beams (:226-272), sequential in selection order
   if (lane == 0) {
-    int n_alive = 0, best_pk = -1, best_tok = 0;
-    float best_score = bs.best_score[b];
-    int best_len = bs.best_len[b];
+    int n_alive = 0, n_jobs = 0;
+    float* ps = bs.best_score + r0;
+    int* pl = bs.best_len + r0;
+    int* pslot = bs.best_slot + r0;
     for (int sel = 0; sel < n_sel; ++sel) {
       const int pk = sm.pk[sel], tok = sm.nt[sel];
       const float v = sm.v[sel];
       if (tok == end_id) {
         const float fin = v / (float)pow((double)(step + 1), (double)length_penalty);   // (len(new_seq)-1)**lp, :238-239
-        if (best_len == 0 || fin > best_score) { best_score = fin; best_len = step + 1; best_pk = pk; best_tok = tok; }
+        // sorted insert; an equal score goes behind the entries already there (first maximum kept, :277-281)
+        int pos = 0;
+        while (pos < K && pl[pos] != 0 && !(fin > ps[pos])) ++pos;
+        if (pos < K) {
+          const int slot = pslot[K - 1];           // slot of the entry that drops out (an empty one while the pool fills)
+          for (int i = K - 1; i > pos; --i) { ps[i] = ps[i - 1]; pl[i] = pl[i - 1]; pslot[i] = pslot[i - 1]; }
+          ps[pos] = fin; pl[pos] = step + 1; pslot[pos] = slot;
+          sm.jslot[n_jobs] = slot;
+          sm.jpk[n_jobs] = pk;
+          ++n_jobs;
+        }
       } else {
         sm.np[n_alive] = pk;
         sm.ns[n_alive] = v;
@@ -414,17 +432,20 @@ __device__ __forceinline__ void beam_select_video(const BeamState& bs, const flo
         ++n_alive;
       }
     }
-    if (best_pk >= 0) { bs.best_score[b] = best_score; bs.best_len[b] = best_len; }
     sm.misc[0] = n_alive;
-    sm.misc[1] = best_pk;
-    sm.misc[2] = best_tok;
+    sm.misc[1] = n_jobs;
     if (n_alive == 0) bs.done[b] = 1;       // :251
   }
   __syncwarp();
-  const int n_alive = sm.misc[0], best_pk = sm.misc[1];
-  if (best_pk >= 0) {
-    for (int i = lane; i < step; i += 32) bs.best_seq[(int64_t)b * S + i] = hin[(int64_t)(r0 + best_pk) * S + i];
-    if (lane == 0) bs.best_seq[(int64_t)b * S + step] = sm.misc[2];
+  const int n_alive = sm.misc[0], n_jobs = sm.misc[1];
+  // tokens of the hypotheses that entered the pool (in completion order: a slot freed and re-used within the step is
+  // simply overwritten by the later job)
+  for (int j = 0; j < n_jobs; ++j) {
+    int* dst = bs.best_seq + (int64_t)(r0 + sm.jslot[j]) * S;
+    const int* src = hin + (int64_t)(r0 + sm.jpk[j]) * S;
+    for (int i = lane; i < step; i += 32) dst[i] = src[i];
+    if (lane == 0) dst[step] = end_id;
+    __syncwarp();
   }
   // token histories of the kept beams: all loads first, then the stores (hin / hout may alias for the compiler, and a
   // load -> store -> load chain per beam costs one memory round trip each)
@@ -699,12 +720,47 @@ __global__ void beam_finalize_kernel(BeamState bs, int B, int K, int S, int step
   const int* hist = bs.hist[steps_run & 1];
   int n;
   const int* src;
-  if (bs.best_len[b] > 0) { n = bs.best_len[b]; src = bs.best_seq + (int64_t)b * S; }
-  else { n = steps_run; src = hist + (int64_t)(b * K) * S; }
+  const int r0 = b * K;
+  if (bs.best_len[r0] > 0) { n = bs.best_len[r0]; src = bs.best_seq + (int64_t)(r0 + bs.best_slot[r0]) * S; }
+  else { n = steps_run; src = hist + (int64_t)r0 * S; }
   out_tokens[(int64_t)b * (S + 1)] = start_id;
   for (int i = 0; i < S; ++i) out_tokens[(int64_t)b * (S + 1) + 1 + i] = (i < n) ? src[i] : start_id;
   out_len[b] = n + 1;
-  if (out_score) out_score[b] = (bs.best_len[b] > 0) ? bs.best_score[b] : bs.scores[b * K];
+  if (out_score) out_score[b] = (bs.best_len[r0] > 0) ? bs.best_score[r0] : bs.scores[r0];
+}
+
+// n-best list of a finished beam decode (the "multiple hypotheses" inference/predictor.py:353 asks for): the video's
+// completed hypotheses in pool order (normalised score descending), then the beams still live after `steps_run` steps in
+// beam order (raw score descending) with score / steps_run^length_penalty; entries beyond what exists have length 0,
+// score -inf and START tokens.  One thread per (video, entry).
+__global__ void beam_nbest_kernel(BeamState bs, int B, int K, int S, int steps_run, int N, int start_id, float length_penalty,
+                                  int* __restrict__ out_tokens /*[B,N,S+1]*/, int* __restrict__ out_len /*[B,N]*/,
+                                  float* __restrict__ out_score /*[B,N]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  const int b = i / N, j = i - b * N, r0 = b * K;
+  int n_done = 0;
+  while (n_done < K && bs.best_len[r0 + n_done] > 0) ++n_done;
+  int n_live = 0;
+  while (n_live < K && bs.alive[r0 + n_live]) ++n_live;      // live beams are compacted to the front
+  int n = 0;
+  float sc = -INFINITY;
+  const int* src = nullptr;
+  if (j < n_done && j < K) {
+    n = bs.best_len[r0 + j];
+    sc = bs.best_score[r0 + j];
+    src = bs.best_seq + (int64_t)(r0 + bs.best_slot[r0 + j]) * S;
+  } else if (j - n_done < n_live) {
+    const int k = j - n_done;
+    n = steps_run;
+    sc = bs.scores[r0 + k] / (float)pow((double)steps_run, (double)length_penalty);
+    src = bs.hist[steps_run & 1] + (int64_t)(r0 + k) * S;
+  }
+  int* dst = out_tokens + (int64_t)i * (S + 1);
+  dst[0] = start_id;
+  for (int t = 0; t < S; ++t) dst[1 + t] = (t < n) ? src[t] : start_id;
+  out_len[i] = (n > 0) ? n + 1 : 0;
+  out_score[i] = sc;
 }
 
 // fp32 -> bf16 conversion for GEMM operands (features, when not consumed as tf32)

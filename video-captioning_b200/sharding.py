@@ -65,7 +65,13 @@ def gather_captions(tokens: torch.Tensor, lengths: torch.Tensor, pad_id: int, gr
 
 class ShardedCaptioner:
     """Data-parallel caption generation: ``generate`` takes this rank's shard (or the full batch with
-    ``already_sharded=False``) and returns the gathered result on every rank."""
+    ``already_sharded=False``) and returns the gathered result on every rank.
+
+    Beam rows are exactly the rows of an unsharded call (row i == the B=1 call on video i).  Greedy: the reference's
+    batched loop stops at the first step where EVERY row of the batch emits END (decoder.py:275), so a shard may stop
+    at an earlier column than the whole batch would; gathered rows are right-padded with END, which decodes to the same
+    caption (``decode_caption`` drops END) but the columns after a row's first END are not those of an unsharded call.
+    A rank whose shard is empty (fewer videos than ranks) contributes zero rows and still takes part in the gather."""
 
     def __init__(self, model, group=None):
         self.model = model
@@ -86,6 +92,7 @@ class ShardedCaptioner:
             lo, hi = shard_bounds(video_features.shape[0], self.world_size, self.rank)
             video_features = video_features[lo:hi]
             video_mask = None if video_mask is None else video_mask[lo:hi]
+        # (an empty shard -- fewer videos than ranks -- yields empty results and still takes part in the gather)
         out = self.model.generate(video_features, start_token_id, end_token_id, max_length=max_length,
                                   video_mask=video_mask, method=method, **kwargs)
         toks = out["generated_tokens"]

@@ -78,6 +78,7 @@ class VideoCaptioningModel(nn.Module):
             raise ValueError(f"precision must be one of {list(_native.PRECISION_IDS)}")
         self.config = config
         self.vocabulary_size = vocabulary_size
+        self._check_dims(precision)
         self.encoder = VideoEncoder(config)
         self.decoder = CaptionDecoder(config, vocabulary_size, attention_type, num_heads)
         self.feature_extractor = None     # CNN extractors are out of scope (precomputed features)
@@ -108,10 +109,39 @@ class VideoCaptioningModel(nn.Module):
         self.encoder._owner = weakref.ref(self)
 
     # ------------------------------------------------------------------ native handle management
+    def _check_dims(self, precision: str) -> None:
+        """Size limits of the native kernels, raised where the model is built rather than at the first generate():
+        F, H, E, A multiples of 8 (vectorised rows), 64 in bf16 mode (tensor-core k-blocks); the vocabulary may have
+        any size (len(vocabulary) is arbitrary in reference checkpoints; it is padded internally)."""
+        m = self.config.model
+        if m.encoder_hidden_dim != m.decoder_hidden_dim:
+            raise ValueError("encoder_hidden_dim != decoder_hidden_dim is not supported: the reference draws a fresh random "
+                             "Linear on every call in that case (decoder.py:97-99), so there is nothing to reproduce")
+        dims = dict(cnn_feature_dim=m.cnn_feature_dim, encoder_hidden_dim=m.encoder_hidden_dim,
+                    embedding_dim=m.embedding_dim, attention_dim=m.attention_dim)
+        mult = 8
+        bad = {k: v for k, v in dims.items() if v <= 0 or v % mult}
+        if precision == "bf16":
+            bad.update({k: v for k, v in dims.items() if k != "attention_dim" and v % 64})
+        if bad:
+            raise ValueError(f"unsupported model dimensions for precision={precision}: {bad} (need multiples of 8; "
+                             "cnn_feature_dim / hidden / embedding multiples of 64 in bf16 mode)")
+        if self.vocabulary_size < 4:
+            raise ValueError("vocabulary_size must be >= 4 (the four special tokens)")
+
     def set_precision(self, precision: str) -> "VideoCaptioningModel":
         if precision not in _native.PRECISION_IDS:
             raise ValueError(f"precision must be one of {list(_native.PRECISION_IDS)}")
+        self._check_dims(precision)
         self.precision = precision
+        return self
+
+    def refresh_native(self) -> "VideoCaptioningModel":
+        """Rebuild the native weight copies.  Needed only after parameters were changed behind autograd's back
+        (``p.data.copy_()`` / ``p.data = ...`` do not bump the tensor version the handle cache watches);
+        ``load_state_dict``, ``.to()`` and in-place ops on the parameters are picked up automatically."""
+        self._native_handle = None
+        self._native_key = None
         return self
 
     def _desc(self) -> Dict[str, int]:
@@ -141,21 +171,41 @@ class VideoCaptioningModel(nn.Module):
     def generate(self, video_features: torch.Tensor, start_token_id: int, end_token_id: int, max_length: int = 20,
                  video_mask: Optional[torch.Tensor] = None, method: str = "greedy", **kwargs) -> Dict[str, torch.Tensor]:
         """video_captioning_model.py:79-125.  kwargs: greedy ``temperature``; beam ``beam_size``,
-        ``length_penalty`` (+ opt-in ``diverse_beams``)."""
+        ``length_penalty``; opt-in, beyond the reference: ``diverse_beams=True`` (real beam search: only beam 0 is
+        live at step 0 instead of K tied copies, :194) and ``num_return_sequences=N`` which adds the n-best lists
+        ``nbest_tokens`` [B,N,L], ``nbest_lengths`` [B,N] (0 = none), ``nbest_scores`` [B,N] (what
+        inference/predictor.py:353 asks the beam to return)."""
         if method not in ("greedy", "beam"):
             raise ValueError(f"Unsupported generation method: {method}")
         if method == "greedy":
             allowed = {"temperature"}
         else:
-            allowed = {"beam_size", "length_penalty", "diverse_beams"}
+            allowed = {"beam_size", "length_penalty", "diverse_beams", "num_return_sequences"}
         bad = set(kwargs) - allowed
         if bad:
             raise TypeError(f"generate(method='{method}') got unexpected keyword arguments {sorted(bad)}")
         h = self._handle()
         B = video_features.shape[0]
+        nbest = int(kwargs.get("num_return_sequences", 0) or 0)
+        if B == 0:     # empty batch (e.g. an empty shard): well-formed empty results, no device work
+            dev = h.device
+            T = video_features.shape[1] if video_features.dim() == 3 else 0
+            if method == "greedy":
+                return {"generated_tokens": torch.zeros(0, 0, dtype=torch.int64, device=dev),
+                        "attention_weights": torch.zeros(0, 0, T, device=dev)}
+            res = {"generated_tokens": torch.zeros(0, 1, dtype=torch.int64, device=dev),
+                   "lengths": torch.zeros(0, dtype=torch.int64, device=dev), "scores": torch.zeros(0, device=dev)}
+            if nbest > 0:
+                res.update(nbest_tokens=torch.zeros(0, nbest, 1, dtype=torch.int64, device=dev),
+                           nbest_lengths=torch.zeros(0, nbest, dtype=torch.int64, device=dev),
+                           nbest_scores=torch.zeros(0, nbest, device=dev))
+            return res
+        if nbest < 0 or nbest > 2 * int(kwargs.get("beam_size", 5)):
+            raise ValueError("num_return_sequences must be in [0, 2*beam_size]")
         gen = lambda x, mk: h.generate(x, start_token_id, end_token_id, max_length, mk, method,
                                        beam_size=kwargs.get("beam_size", 5), length_penalty=kwargs.get("length_penalty", 1.0),
-                                       temperature=kwargs.get("temperature", 1.0), diverse=kwargs.get("diverse_beams", False))
+                                       temperature=kwargs.get("temperature", 1.0), diverse=kwargs.get("diverse_beams", False),
+                                       nbest=nbest)
         if video_features.device.type == "cpu":
             can_pack = self.precision == "bf16" and video_features.dtype == torch.float32 and video_features.dim() == 3
             if can_pack:
@@ -180,7 +230,13 @@ class VideoCaptioningModel(nn.Module):
         lens = torch.cat([o[1] for o in outs], dim=0)
         scores = torch.cat([o[2] for o in outs], dim=0)
         L = int(lens.max())
-        return {"generated_tokens": tokens[:, :L].to(torch.int64), "lengths": lens.to(torch.int64), "scores": scores}
+        res = {"generated_tokens": tokens[:, :L].to(torch.int64), "lengths": lens.to(torch.int64), "scores": scores}
+        if nbest > 0:
+            nl = torch.cat([o[5] for o in outs], dim=0)
+            Ln = max(1, int(nl.max()))
+            res.update(nbest_tokens=torch.cat([o[4] for o in outs], dim=0)[:, :, :Ln].to(torch.int64),
+                       nbest_lengths=nl.to(torch.int64), nbest_scores=torch.cat([o[6] for o in outs], dim=0))
+        return res
 
     def _generate_from_host(self, h, feats: torch.Tensor, mask, gen):
         """Feature ingest for HOST tensors (predictor.py:101-107 does one blocking H2D per video): the batch is
@@ -376,8 +432,10 @@ class VideoCaptioningModel(nn.Module):
                         rdy.record(copy)
                         compute.wait_event(rdy)
                         clo, chi = chunks[ci]
-                        mk = None if mask is None else mask[clo:chi].to(dev, non_blocking=True)
                         with torch.cuda.stream(compute):
+                            # the mask is transferred on the COMPUTE stream: its consumers (lengths, encoder, every
+                            # attention step) run there, and its memory then belongs to that stream's allocator pool
+                            mk = None if mask is None else mask[clo:chi].to(dev, non_blocking=True)
                             outs[clo] = gen(st["dev16"][clo - w0: chi - w0], mk)
                             fr = torch.cuda.Event()
                             fr.record(compute)
