@@ -424,7 +424,7 @@ def main():
         roof["traffic"] = tr["classes"][dom]["dram_bytes_per_launch"]
         roof["traffic_source"] = tr["file"]
     if "tanh" in work.get(dom, {}):
-        # Bahdanau scoring is bound by the special-function pipe (16 tanh / clk / SM, measured with scratch/mufu_bench.cu),
+        # Bahdanau scoring is bound by the special-function pipe (16 tanh / clk / SM, measured with scripts/mufu_bench.cu),
         # not by HBM: report that roofline as well
         sm_hz = ((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0) * 1e6
         xu_peak = 16.0 * torch.cuda.get_device_properties(dev).multi_processor_count * sm_hz
