@@ -13,7 +13,11 @@ beam-5, 1024 MSVD-shape videos (80 x 4096 features, H=E=A=512, V=10k, max_len 20
            are inside the timed region.
 `roofline`: for the kernel class with the largest share of device time, measured with CUDA events on
            the launching stream in an instrumented pass of the same workload (vc_profile_begin/end).
-`cpu_baseline`: the oracle port of the reference timed on the host cores on a bounded sample.
+`cpu_baseline`: the reference itself (oracle/_ref: the unmodified model files, vendored by __graft_entry__.build();
+           `kind` "reference") -- or, where that copy is absent, the oracle port (`kind` "port") -- timed on the host
+           cores on a bounded sample, one B=1 call per video as predict.py batch does.
+`sustained`: the same device-resident step repeated back to back for >= 2 s (clocks sampled under load).
+`other_configs`: short runs of BASELINE.json configs[0], [2], [3], [4] at their stated sizes (N=1 only).
 Weights are random-init (oracle.synth, reference layout/initialiser distributions); data synthetic.
 """
 from __future__ import annotations
@@ -44,6 +48,9 @@ WORKLOADS = {
     "c3_luong_dot_h1024": dict(shape="c3", attention="luong_dot", method="beam", K=5, S=20, B=1024, precision="bf16"),
     "c4_multihead_resnet": dict(shape="c4", attention="multihead", method="beam", K=3, S=20, B=1024, precision="bf16"),
     "c5_vocab30k_len30": dict(shape="c5", attention="bahdanau", method="beam", K=5, S=30, B=1024, precision="bf16"),
+    # BASELINE configs[4] as written: 65 536 videos in total, sharded over the ranks (strong scaling)
+    "c5_sharded_65536": dict(shape="c5", attention="bahdanau", method="beam", K=5, S=30, B=65536, precision="bf16",
+                             total=True),
 }
 DEFAULT_WORKLOAD = "c2_beam5_msvd_bf16"
 
@@ -170,6 +177,11 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        return self.window(t0, t1)
+
+    def window(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, line in self.rows:
@@ -206,27 +218,49 @@ class ClockSampler:
         return out
 
 
-# ---------------------------------------------------------------------------- CPU arm (oracle port of the reference)
+# ---------------------------------------------------------------------------- CPU arm (the reference on the host cores)
 def cpu_reference_run(wl, n_videos, threads=None):
-    """Times the reference algorithm (oracle port) on the host cores.  Beam is run the way the reference's
-    predict.py batch really runs it: one B=1 call per video (predictor.py:217,464; the batched call raises
-    on staggered END).  Returns (captions/s, seconds, threads)."""
-    from oracle import synth
-    from oracle.caption_oracle import CaptionOracle
+    """Times the reference's own CPU path on the host cores: the UNMODIFIED reference modules (oracle/_ref, or
+    /root/reference where mounted) when present -- `VideoCaptioningModel.generate` called once per video with B=1, which
+    is what predict.py batch does (predictor.py:102,217,464; a batched beam call raises on staggered END) --
+    else the oracle port run the same way.  Returns (captions/s, seconds, threads, kind)."""
+    from oracle import ref_shim, synth
     torch.set_num_threads(threads or os.cpu_count() or 1)
     cfg = synth.make_config(wl["shape"])
     V = cfg.model.vocab_size
     sd = synth.make_state_dict(cfg, V, wl["attention"], seed=0)
     feats = synth.make_features(n_videos, cfg.model.video_sequence_length, cfg.model.cnn_feature_dim, seed=1)
-    o = CaptionOracle(sd)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        if wl["method"] == "beam":
-            o.beam(feats, START, END, max_length=wl["S"], beam_size=wl["K"])
-        else:
-            o.greedy(feats, START, END, max_length=wl["S"])
-    dt = time.perf_counter() - t0
-    return n_videos / dt, dt, torch.get_num_threads()
+    kw = dict(beam_size=wl["K"], length_penalty=1.0) if wl["method"] == "beam" else {}
+    if ref_shim.available():
+        kind = "reference"
+        model = ref_shim.build_reference_model(cfg, V, wl["attention"], state_dict=sd)
+        x = torch.from_numpy(feats)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            for b in range(n_videos):       # predictor.py:102: unsqueeze(0) -> B = 1
+                model.generate(x[b:b + 1], START, END, max_length=wl["S"], method=wl["method"], **kw)
+        dt = time.perf_counter() - t0
+    else:
+        kind = "port"
+        from oracle.caption_oracle import CaptionOracle
+        o = CaptionOracle(sd)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            for b in range(n_videos):
+                if wl["method"] == "beam":
+                    o.beam(feats[b:b + 1], START, END, max_length=wl["S"], beam_size=wl["K"])
+                else:
+                    o.greedy(feats[b:b + 1], START, END, max_length=wl["S"])
+        dt = time.perf_counter() - t0
+    return n_videos / dt, dt, torch.get_num_threads(), kind
+
+
+def cpu_sample_text(n, dt, kind, wl):
+    from oracle import ref_shim
+    where = "oracle/_ref, the vendored copy" if ref_shim.is_vendored_copy() else ref_shim.REF_ROOT
+    what = (f"the unmodified reference ({where}), VideoCaptioningModel.generate" if kind == "reference"
+            else "oracle port of the reference")
+    return f"{n} videos ({dt:.1f} s), {what}, one B=1 {wl['method']} call per video as predict.py batch does"
 
 
 def run_reference_arm(args, wl, wl_name):
@@ -235,19 +269,20 @@ def run_reference_arm(args, wl, wl_name):
         return
     n = args.cpu_videos
     vals = []
-    for _ in range(args.warmup and 1):
-        cpu_reference_run(wl, max(2, n // 4))
+    n_warm = 1 if args.warmup else 0
+    for _ in range(n_warm):
+        cpu_reference_run(wl, max(2, n // 8))
     for _ in range(max(1, min(args.steps, 3))):
-        v, dt, th = cpu_reference_run(wl, n)
-        vals.append((v, dt))
+        vals.append(cpu_reference_run(wl, n))
     v = float(np.median([x[0] for x in vals]))
     dt = float(np.median([x[1] for x in vals]))
+    th, kind = vals[0][2], vals[0][3]
     line = {"impl": "reference", "metric": "captions/sec", "value": v, "unit": "captions/s", "n_gpus": args.gpus,
-            "steps": len(vals), "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": len(vals), "warmup": n_warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl_name, "sample_videos": n, **{k: wl[k] for k in ("method", "K", "S", "attention")}},
-            "cpu_baseline": {"value": v, "unit": "captions/s", "cores": th, "kind": "port",
-                             "sample": f"{n} videos per step, oracle port of the reference run per video (B=1) as predict.py batch does"},
+            "cpu_baseline": {"value": v, "unit": "captions/s", "cores": th, "kind": kind,
+                             "sample": cpu_sample_text(n, dt, kind, wl) + " (per step)"},
             "e2e": {"value": v, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -262,7 +297,10 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="videos per GPU per step (default: workload's)")
     ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
-    ap.add_argument("--cpu-videos", type=int, default=512, help="bounded CPU-baseline sample (videos)")
+    ap.add_argument("--cpu-videos", type=int, default=128, help="bounded CPU-baseline sample (videos), both arms")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--sweep-json", default=None, help="also write the other-configs sweep here")
+    ap.add_argument("--min-sustained-s", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-class device-time breakdown here")
     args = ap.parse_args()
@@ -280,55 +318,56 @@ def main():
     import video_captioning_b200 as vc
     from oracle import synth   # synthetic weights/features only (shared recipe); never on the timed path
     from video_captioning_b200 import _native
+    from video_captioning_b200.affinity import bind_to_gpu_numa
     from video_captioning_b200.sharding import gather_captions_equal
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host side of the ingest (pinned buffers, packer threads) on the GPU's NUMA node / this rank's share of the cores
+    affinity = bind_to_gpu_numa(local_rank, local_world, local_rank) if world > 1 else {"bound": False}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = synth.make_config(wl["shape"])
+    strong = bool(wl.get("total"))
+    if strong:       # a fixed total split over the ranks (BASELINE configs[4])
+        assert wl["B"] % world == 0
+        wl["B"] = wl["B"] // world
+
+    def setup(w, seed):
+        cfg = synth.make_config(w["shape"])
+        cm = cfg.model
+        sd = synth.make_state_dict(cfg, cm.vocab_size, w["attention"], seed=0)
+        model = vc.VideoCaptioningModel(cfg, cm.vocab_size, attention_type=w["attention"], precision=w["precision"],
+                                        chunk_size=min(w["B"], 2048))
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        model = model.to(dev).eval()
+        # synthetic features generated on the device (per-rank seed), in slabs: resident in HBM before any timed region
+        g = torch.Generator(device=dev).manual_seed(seed)
+        feats = torch.empty(w["B"], cm.video_sequence_length, cm.cnn_feature_dim, device=dev, dtype=torch.float32)
+        for lo in range(0, w["B"], 1024):
+            feats[lo:lo + 1024].normal_(generator=g)
+        return cfg, model, feats
+
+    cfg, model, feats = setup(wl, 1234 + rank)
     cm = cfg.model
     V, T, F = cm.vocab_size, cm.video_sequence_length, cm.cnn_feature_dim
     B, K, S = wl["B"], wl["K"], wl["S"]
-    sd = synth.make_state_dict(cfg, V, wl["attention"], seed=0)
-    model = vc.VideoCaptioningModel(cfg, V, attention_type=wl["attention"], precision=wl["precision"], chunk_size=B)
-    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
-    model = model.to(dev).eval()
-    # synthetic features generated on the device (per-rank seed): resident in HBM before the timed region
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    feats = torch.randn(B, T, F, generator=g, device=dev, dtype=torch.float32)
     kw = dict(beam_size=K, length_penalty=1.0) if wl["method"] == "beam" else {}
 
-    def step(x):
-        return model.generate(x, START, END, max_length=S, method=wl["method"], **kw)
+    def step(x, m=model, w=wl, k=kw):
+        return m.generate(x, START, END, max_length=w["S"], method=w["method"], **k)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        out = step(feats)
-    barrier()
-
-    # ---- timed region (device-resident inputs); inputs (1.3 GB at B=1024) far exceed the 126 MB L2
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler is not None:
-        sampler.wait_ready()
-    time.sleep(0.1)
-    l0 = _native.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0 = time.time()
-    e0.record()
-    torch.cuda.nvtx.range_push("timed")     # ncu --nvtx --nvtx-include "timed/" profiles exactly these steps
-    for _ in range(args.steps):
-        out = step(feats)
+    def gather(out):
         if world > 1:   # the path's only collective: final caption gather (latency-bound, fixed [B, S+2] shape)
             tk = out["generated_tokens"]
             width = S + 1 if wl["method"] == "beam" else S
@@ -336,26 +375,62 @@ def main():
                 tk = torch.nn.functional.pad(tk, (0, width - tk.shape[1]), value=START)
             ln = out["lengths"] if "lengths" in out else torch.full((B,), tk.shape[1], device=dev)
             gather_captions_equal(tk, ln)
-    torch.cuda.nvtx.range_pop()
-    e1.record()
+
+    def timed(n_steps):
+        """n_steps back-to-back steps bracketed by barrier + synchronize; CUDA events; max over ranks -> (ms, t0, t1)"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.time()
+        e0.record()
+        for _ in range(n_steps):
+            gather(step(feats))
+        e1.record()
+        barrier()
+        t1 = time.time()
+        tms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        return float(tms.item()), t0, t1
+
+    for _ in range(max(args.warmup, 3)):
+        out = step(feats)
     barrier()
-    t1 = time.time()
-    ms = e0.elapsed_time(e1)
+
+    # ---- sustained pass: the step repeated back to back for >= min_sustained_s.  It is a measurement of its own (clocks
+    # sampled under seconds of load) and it brings the GPU to its steady state before the K timed steps, which would
+    # otherwise be ~0.15 s of burst clocks on an idle box.
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.wait_ready()
+    probe_ms, _, _ = timed(2)
+    n_sus = max(args.steps, int(np.ceil(args.min_sustained_s * 1e3 / max(probe_ms / 2, 1e-3))))
+    if world > 1:
+        t = torch.tensor([n_sus], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_sus = int(t.item())
+    sus_ms, st0, st1 = timed(n_sus)
+    sus_clocks = sampler.window(st0, st1) if sampler else None
+
+    # ---- timed region: EXACTLY K steps, device-resident inputs (B*T*F*4 bytes, far larger than the 126 MB L2)
+    l0 = _native.launch_count()
+    torch.cuda.nvtx.range_push("timed")     # ncu --nvtx --nvtx-include "timed/" profiles exactly these steps
+    ms, t0, t1 = timed(args.steps)
+    torch.cuda.nvtx.range_pop()
     launches = _native.launch_count() - l0
     clocks = sampler.stop(t0, t1) if sampler else None
-    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
     value = world * B * args.steps / (ms * 1e-3)
+    sustained = {"value": world * B * n_sus / (sus_ms * 1e-3), "unit": "captions/s", "steps_run": n_sus,
+                 "seconds": sus_ms * 1e-3, "clocks": sus_clocks}
 
-    # ---- e2e through the public API with host buffers
-    host = torch.empty(B, T, F, dtype=torch.float32).pin_memory()
-    host.copy_(feats.cpu())
+    # ---- e2e through the public API with HOST (pinned) fp32 features: H2D inside the timed region, D2H of the results
+    Be = min(B, 2048)
+    host = torch.empty(Be, T, F, dtype=torch.float32).pin_memory()
+    host.copy_(feats[:Be].cpu())
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(2):
-        o = step(host)          # pinned host tensor: generate() streams it in chunks overlapped with compute
+        o = step(host)          # pinned host tensor: generate() streams it in pieces overlapped with compute
         _ = o["generated_tokens"].cpu()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     d2h = 0
@@ -371,14 +446,53 @@ def main():
     ems = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / (float(ems.item()) * 1e-3)
+    e2e_value = world * Be * e2e_steps / (float(ems.item()) * 1e-3)
     # bf16 mode: part of the batch is rounded to bf16 on the host cores and crosses the link at half the size
     # (VideoCaptioningModel._generate_from_host_packed); the bytes are those of the last step's actual copies
     h2d = int(getattr(model, "host_stats", {}).get("h2d_bytes", 0)) or int(host.numel() * 4)
+    packing = bool(getattr(model, "host_pack", False)) and wl["precision"] == "bf16"
+    # the ingest's own roofline: H2D rate of one pinned 1 GiB copy per rank, all ranks at once, and the host cores' packing
+    # rate (fp32 bytes consumed per second), measured here; ceiling = the captions/s the faster of "all fp32 over the link"
+    # and "the best raw/packed split" could reach if nothing else took time
+    probe = torch.empty(1 << 28, dtype=torch.float32).pin_memory()
+    dprobe = torch.empty_like(probe, device=dev)
+    dprobe.copy_(probe, non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(2):
+        dprobe.copy_(probe, non_blocking=True)
+    e1.record()
+    barrier()
+    lms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(lms, op=dist.ReduceOp.MAX)
+    link_gbs = 2 * probe.numel() * 4 / (float(lms.item()) * 1e-3) / 1e9
+    pack_gbs = None
+    if packing:
+        dst16 = torch.empty(probe.numel() // 4, dtype=torch.bfloat16).pin_memory()
+        src32 = probe[: probe.numel() // 4]
+        _native.host_pack_bf16(src32, dst16, model.host_pack_threads)
+        tp = time.perf_counter()
+        _native.host_pack_bf16(src32, dst16, model.host_pack_threads)
+        pack_gbs = src32.numel() * 4 / (time.perf_counter() - tp) / 1e9
+        del dst16
+    del probe, dprobe
+    per_cap = T * F * 4.0                          # fp32 bytes of one video
+    ceil_plain = world * link_gbs * 1e9 / per_cap
+    ceiling = ceil_plain
+    if pack_gbs:
+        # a fraction r of the videos crosses raw (4 B/elem), 1-r packed (2 B/elem over the link, 4 B/elem through the cores):
+        # time per video = max(link: (r + (1-r)/2) * per_cap / L, cores: (1-r) * per_cap / P); best r equalises the two
+        L_, P_ = link_gbs * 1e9, pack_gbs * 1e9
+        r = max(0.0, min(1.0, (2 * L_ - P_) / (2 * L_ + P_)))
+        ceiling = world / max((r + (1 - r) / 2) * per_cap / L_, (1 - r) * per_cap / P_)
     e2e = {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
-           "host_bytes_per_step": int(host.numel() * 4),
+           "host_bytes_per_step": int(host.numel() * 4), "videos_per_gpu_per_step": Be,
+           "link_gbs": link_gbs, "host_pack_gbs": pack_gbs, "ceiling": ceiling, "ceiling_fp32_link_only": ceil_plain,
+           "frac_of_ceiling": e2e_value / ceiling, "affinity": affinity,
            "ingest": ("fp32 host features; pieces go raw (fp32 H2D + device rounding) or host-packed to bf16 (host cores, "
                       f"{getattr(model, 'host_pack_threads', 0)} threads), whichever route is free") if h2d != host.numel() * 4 else "fp32 H2D"}
+    del host
 
     if rank != 0:
         if world > 1:
@@ -431,22 +545,71 @@ def main():
         ach = work[dom]["tanh"] / (d["ms_per_step"] * 1e-3)
         roof["xu"] = {"bound": "mufu", "achieved": ach, "peak": xu_peak, "unit": "tanh/s", "frac": ach / xu_peak,
                       "note": "peak = 16 MUFU results/clk/SM x SMs x sampled SM clock"}
+    # every class against its own bound (tensor classes: sustained bf16 peak; the others: HBM)
+    for cls, ent in breakdown.items():
+        if cls in TENSOR_CLASSES and wl["precision"] == "bf16":
+            ent["frac"] = ent["tflops"] / peaks["tf_sus"]
+            ent["bound"] = "tensor"
+        else:
+            ent["frac"] = ent["gbs"] / peaks["hbm"]
+            ent["bound"] = "hbm"
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        v, dt, th = cpu_reference_run(wl, args.cpu_videos)
-        cpu = {"value": v, "unit": "captions/s", "cores": th, "kind": "port",
-               "sample": f"{args.cpu_videos} videos ({dt:.1f} s), oracle port of the reference, one B=1 {wl['method']} call per video"}
+        v, dt, th, kind = cpu_reference_run(wl, args.cpu_videos)
+        cpu = {"value": v, "unit": "captions/s", "cores": th, "kind": kind,
+               "sample": cpu_sample_text(args.cpu_videos, dt, kind, wl)}
+
+    # ---- the other BASELINE configs at their stated sizes, short runs (N=1, default workload only)
+    other = None
+    if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_sweep and not args.batch:
+        del feats, model
+        torch.cuda.empty_cache()
+        other = {}
+        sweep = [("configs[0] greedy B=32 fp32", dict(WORKLOADS["c1_greedy_msvd_fp32"])),
+                 ("configs[2] Luong general H=1024 beam-5 B=4096", dict(WORKLOADS["c3_luong_general_h1024"], B=4096)),
+                 ("configs[2] Luong dot H=1024 beam-5 B=4096", dict(WORKLOADS["c3_luong_dot_h1024"], B=4096)),
+                 ("configs[3] multi-head(8) ResNet 2048-d T=40 beam-3, 3 captions per video B=1024",
+                  dict(WORKLOADS["c4_multihead_resnet"], multiple=3)),
+                 ("configs[4] V=30k max_len 30 beam-5, one 8192-video shard (the per-GPU share of 65536 at N=8)",
+                  dict(WORKLOADS["c5_vocab30k_len30"], B=8192))]
+        for name, w in sweep:
+            try:
+                _, m2, f2 = setup(w, 99)
+                k2 = dict(beam_size=w["K"], length_penalty=1.0) if w["method"] == "beam" else {}
+                if w.get("multiple"):      # predict.py multiple: n-best from one real beam search (opt-in mode)
+                    k2.update(diverse_beams=True, num_return_sequences=w["multiple"])
+                for _ in range(3):
+                    step(f2, m2, w, k2)
+                torch.cuda.synchronize()
+                e0.record()
+                n2 = 5
+                for _ in range(n2):
+                    step(f2, m2, w, k2)
+                e1.record()
+                torch.cuda.synchronize()
+                ms2 = e0.elapsed_time(e1) / n2
+                other[name] = {"value": w["B"] / (ms2 * 1e-3), "unit": "captions/s", "ms_per_step": ms2, "videos": w["B"],
+                               "dtype": w["precision"], "steps": n2}
+                del m2, f2
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001 -- a sweep entry must not take the headline line down
+                other[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if args.sweep_json:
+            with open(args.sweep_json, "w") as f:
+                json.dump(other, f, indent=1)
 
     line = {"metric": "captions/sec", "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": wl["precision"], "data": "synthetic",
             "config": {"workload": args.workload, "videos_per_gpu_per_step": B, "frames": T, "feature_dim": F,
                        "hidden": cm.encoder_hidden_dim, "vocab": V, "method": wl["method"], "beam": K, "max_len": S,
                        "attention": wl["attention"], "l2": "inputs (B*T*F*4 bytes) larger than L2, no flush needed",
-                       "sharding": f"dp{world}: videos split over ranks, final NCCL all_gather of tokens"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "breakdown": breakdown}
+                       "sharding": f"dp{world}: videos split over ranks, final NCCL all_gather of tokens",
+                       "preload": f"{n_sus} untimed back-to-back steps ({sus_ms * 1e-3:.2f} s, reported as `sustained`) right before the timed steps"},
+            "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+            "cpu_baseline": cpu, "breakdown": breakdown, "other_configs": other}
     print(json.dumps(line), flush=True)
     if args.profile_json:
         with open(args.profile_json, "w") as f:

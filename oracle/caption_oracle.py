@@ -241,7 +241,7 @@ class CaptionOracle:
 
         Returns a dict: ``best`` (tokens incl. leading START), ``best_score`` (normalised score of the best
         completed hypothesis, else the raw score of live beam 0, :274-286), ``step_scores`` (per-step top-K
-        candidate scores), ``nbest`` = [(tokens, score)]: completed hypotheses by normalised score
+        candidate scores), ``nbest`` = [(tokens, score)]: the K best completed hypotheses by normalised score
         (descending, first-completed first among equals -- what ``max`` at :277-281 keeps), followed by the
         beams still live after ``max_length`` steps (score / generated_length ** length_penalty).
         """
@@ -288,7 +288,7 @@ class CaptionOracle:
             best, best_score = max(completed, key=lambda x: x[1])
         else:
             best, best_score = seqs[0], float(scores[0])                      # :286
-        nbest = sorted(completed, key=lambda x: -x[1])                        # stable: first-completed first among equals
+        nbest = sorted(completed, key=lambda x: -x[1])[:K]                    # stable: first-completed first among equals
         if live:
             gen = seqs.shape[1] - 1
             nbest += [(seqs[k], float(scores[k]) / (gen ** length_penalty)) for k in range(seqs.shape[0])]

@@ -15,13 +15,47 @@ import sys
 import types
 from types import SimpleNamespace
 
-REF_ROOT = os.environ.get("VC_REFERENCE_ROOT", "/root/reference")
+# Where the unmodified reference sources are read from: $VC_REFERENCE_ROOT, else /root/reference (the build container),
+# else oracle/_ref -- a git-ignored, byte-identical copy of the five files this shim executes, made by
+# ``vendor_reference()`` (called from __graft_entry__.build() where /root/reference exists) so that bench.py's
+# ``--impl reference`` arm can time the reference itself on the GPU box, where /root/reference does not exist.
+_VENDOR_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+_VENDORED = ("src/models/attention.py", "src/models/encoder.py", "src/models/decoder.py",
+             "src/models/video_captioning_model.py", "src/data/vocabulary.py")
+
+
+def _pick_root() -> str:
+    cands = [os.environ.get("VC_REFERENCE_ROOT"), "/root/reference", _VENDOR_ROOT]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "src", "models", "video_captioning_model.py")):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _pick_root()
 _REF_SRC = os.path.join(REF_ROOT, "src")
 _loaded = {}
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(_REF_SRC, "models", "video_captioning_model.py"))
+
+
+def is_vendored_copy() -> bool:
+    return os.path.abspath(REF_ROOT) == os.path.abspath(_VENDOR_ROOT)
+
+
+def vendor_reference(src_root: str = "/root/reference") -> bool:
+    """Copy the five reference files this shim executes, unmodified, into oracle/_ref (git-ignored; it travels to the
+    GPU box with the working tree like the built .so).  Returns False where the reference is not mounted."""
+    import shutil
+    if not os.path.isfile(os.path.join(src_root, "src", "models", "video_captioning_model.py")):
+        return False
+    for rel in _VENDORED:
+        dst = os.path.join(_VENDOR_ROOT, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(src_root, rel), dst)
+    return True
 
 
 def _pkg(name: str) -> None:
