@@ -37,7 +37,7 @@ enum { VC_ATTN_BAHDANAU = 0, VC_ATTN_LUONG_DOT = 1, VC_ATTN_LUONG_GENERAL = 2, V
 enum { VC_PREC_FP32 = 0, VC_PREC_BF16 = 1 };
 enum { VC_METHOD_GREEDY = 0, VC_METHOD_BEAM = 1 };
 /* element type of a feature buffer handed to vc_generate_ex */
-enum { VC_DTYPE_F32 = 0, VC_DTYPE_BF16 = 1 };
+enum { VC_DTYPE_F32 = 0, VC_DTYPE_BF16 = 1, VC_DTYPE_F16 = 2 /* host staging only */ };
 
 /* Mirrors the config.model.* attributes the path reads (config/config.py:13-31). */
 typedef struct {
@@ -152,6 +152,13 @@ int vc_generate(vc_model_t* m, const float* feats, int32_t B, int32_t T, const i
  *   vc_generate_ex     vc_generate with the feature element type stated (VC_DTYPE_BF16 only in VC_PREC_BF16 mode)
  */
 int vc_host_pack_bf16(const float* src, uint16_t* dst, size_t n, int32_t threads);
+/*   vc_host_stage_rows  host: the Predictor's per-video `torch.FloatTensor(features)` + `_resize_features`
+ *                       (inference/predictor.py:101-107, :292-315; data/dataset.py:124-150) for a whole batch in one pass:
+ *                       row r of dst [n_rows, F] = the source frame src_rows[r] points at (host address as uint64; the frame
+ *                       the linspace subsampling selects) or zeros where src_rows[r] == 0 (zero padding), converted
+ *                       src_dtype -> dst_dtype on the way (VC_DTYPE_*: f32->f32, f32->bf16 RNE, f16->f16 / bf16 / f32). */
+int vc_host_stage_rows(const uint64_t* src_rows, int64_t n_rows, int64_t F, int32_t src_dtype, void* dst, int32_t dst_dtype,
+                       int32_t threads);
 int vc_convert_bf16(const float* src_dev, void* dst_dev, int64_t n, vc_stream_t stream);
 int vc_generate_ex(vc_model_t* m, const void* feats, int32_t feats_dtype, int32_t B, int32_t T, const int32_t* frame_lengths,
                    const float* mask, const vc_decode_params_t* p, int32_t* tokens, int32_t* lengths, float* scores,

@@ -37,7 +37,7 @@ PRECISION_IDS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 EXPORTED_SYMBOLS = (
     "vc_last_error", "vc_version", "vc_launch_count", "vc_profile_begin", "vc_profile_end", "vc_model_create", "vc_model_set_weight", "vc_model_finalize",
     "vc_model_destroy", "vc_workspace_bytes", "vc_encoder_forward", "vc_attn_precompute",
-    "vc_decode_greedy", "vc_decode_beam", "vc_beam_nbest", "vc_generate", "vc_generate_ex", "vc_host_pack_bf16", "vc_convert_bf16",
+    "vc_decode_greedy", "vc_decode_beam", "vc_beam_nbest", "vc_generate", "vc_generate_ex", "vc_host_pack_bf16", "vc_host_stage_rows", "vc_convert_bf16",
     "vc_forward_teacher", "vc_linear",
     "vc_attention_step", "vc_beam_select",
 )
@@ -146,6 +146,7 @@ def load_library() -> ctypes.CDLL:
         lib.vc_generate_ex.argtypes = [vp, vp, i32, i32, i32, i32p, f32p, ctypes.POINTER(DecodeParams), i32p, i32p, f32p,
                                        f32p, vp, sz, vp]
         lib.vc_host_pack_bf16.argtypes = [vp, vp, sz, i32]
+        lib.vc_host_stage_rows.argtypes = [vp, i64, i64, i32, vp, i32, i32]
         lib.vc_convert_bf16.argtypes = [f32p, vp, i64, vp]
         lib.vc_forward_teacher.argtypes = [vp, f32p, i32, i32, i32p, f32p, i32p, i32, f32p, f32p, f32p, vp, sz, vp]
         lib.vc_linear.argtypes = [i32, f32p, f32p, f32p, f32p, i32, i32, i32, i32, vp, sz, vp]
@@ -426,6 +427,21 @@ def host_pack_bf16(src: torch.Tensor, dst: torch.Tensor, threads: int) -> None:
         raise ValueError("host_pack_bf16: contiguous buffers of equal length expected")
     check(load_library().vc_host_pack_bf16(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), src.numel(),
                                            int(threads)), "vc_host_pack_bf16")
+
+
+_STAGE_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def host_stage_rows(src_rows, n_rows: int, F: int, src_dtype: torch.dtype, dst: torch.Tensor, threads: int) -> None:
+    """dst (host [n_rows, F], contiguous) row r = the F-element source frame at host address src_rows[r] (numpy uint64
+    array; 0 = zero row), converted src_dtype -> dst.dtype (vc_host_stage_rows)."""
+    if dst.device.type != "cpu" or not dst.is_contiguous() or dst.numel() != n_rows * F:
+        raise ValueError("host_stage_rows: contiguous host destination of n_rows*F elements expected")
+    if src_rows.dtype.name != "uint64" or src_rows.size != n_rows or not src_rows.flags["C_CONTIGUOUS"]:
+        raise ValueError("host_stage_rows: src_rows must be a contiguous uint64 array of n_rows addresses")
+    check(load_library().vc_host_stage_rows(ctypes.c_void_p(src_rows.ctypes.data), int(n_rows), int(F),
+                                            _STAGE_DTYPES[src_dtype], ctypes.c_void_p(dst.data_ptr()),
+                                            _STAGE_DTYPES[dst.dtype], int(threads)), "vc_host_stage_rows")
 
 
 def convert_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:

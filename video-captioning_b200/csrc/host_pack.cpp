@@ -135,3 +135,69 @@ extern "C" int vc_host_pack_bf16(const float* src, uint16_t* dst, size_t n, int3
   });
   return 0;
 }
+
+// ---------------------------------------------------------------- batched resize / pad gather into a staging buffer
+// predictor.py:101-107 + :292-315 + data/dataset.py:124-150 for a whole batch: row r of the [n_rows, F] staging buffer
+// (n_rows = videos x target frames) is a copy of the source frame src_rows[r] points at (the frame the reference's
+// linspace subsampling selects), or zeros where src_rows[r] == 0 (zero padding of a short video).  The copy converts on
+// the fly: fp32 -> fp32 (plain), fp32 -> bf16 (round to nearest even: the packed ingest, half the bytes over the link),
+// fp16 -> fp16 (features stored as halves are staged without widening).  One pass over the selected source frames only --
+// frames the subsampling drops are never touched.  dtype codes: 0 = fp32, 1 = bf16, 2 = fp16.
+namespace {
+inline float half_to_float(uint16_t h) {
+  const uint32_t s = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+  uint32_t x;
+  if (e == 0) {
+    if (m == 0) x = s;
+    else {       // subnormal
+      int sh = 0;
+      uint32_t mm = m;
+      while ((mm & 0x400u) == 0) { mm <<= 1; ++sh; }
+      x = s | ((uint32_t)(113 - sh) << 23) | ((mm & 0x3ffu) << 13);
+    }
+  } else if (e == 31) x = s | 0x7f800000u | (m << 13);
+  else x = s | ((e + 112) << 23) | (m << 13);
+  float f;
+  memcpy(&f, &x, 4);
+  return f;
+}
+}  // namespace
+
+extern "C" int vc_host_stage_rows(const uint64_t* src_rows, int64_t n_rows, int64_t F, int32_t src_dtype, void* dst,
+                                  int32_t dst_dtype, int32_t threads) {
+  if (src_rows == nullptr || dst == nullptr || n_rows < 0 || F <= 0) return 1;
+  const bool f32_f32 = src_dtype == 0 && dst_dtype == 0, f32_b16 = src_dtype == 0 && dst_dtype == 1;
+  const bool f16_f16 = src_dtype == 2 && dst_dtype == 2, f16_b16 = src_dtype == 2 && dst_dtype == 1, f16_f32 = src_dtype == 2 && dst_dtype == 0;
+  if (!(f32_f32 || f32_b16 || f16_f16 || f16_b16 || f16_f32)) return 1;
+  const size_t dst_es = dst_dtype == 0 ? 4 : 2;
+  const bool wide = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+  auto run = [=](int64_t lo, int64_t hi) {
+    for (int64_t r = lo; r < hi; ++r) {
+      uint8_t* d = reinterpret_cast<uint8_t*>(dst) + (size_t)r * F * dst_es;
+      const void* s = reinterpret_cast<const void*>(static_cast<uintptr_t>(src_rows[r]));
+      if (s == nullptr) { memset(d, 0, (size_t)F * dst_es); continue; }
+      if (f32_f32) memcpy(d, s, (size_t)F * 4);
+      else if (f16_f16) memcpy(d, s, (size_t)F * 2);
+      else if (f32_b16) {
+        if (wide) pack_avx512(reinterpret_cast<const float*>(s), reinterpret_cast<uint16_t*>(d), (size_t)F);
+        else pack_scalar(reinterpret_cast<const float*>(s), reinterpret_cast<uint16_t*>(d), (size_t)F);
+      } else {
+        const uint16_t* hs = reinterpret_cast<const uint16_t*>(s);
+        if (f16_f32) { float* o = reinterpret_cast<float*>(d); for (int64_t i = 0; i < F; ++i) o[i] = half_to_float(hs[i]); }
+        else { uint16_t* o = reinterpret_cast<uint16_t*>(d); for (int64_t i = 0; i < F; ++i) o[i] = pack_one(half_to_float(hs[i])); }
+      }
+    }
+  };
+  if (threads < 1) threads = 1;
+  if (threads == 1 || n_rows * F < ((int64_t)1 << 16)) {
+    run(0, n_rows);
+    return 0;
+  }
+  const int64_t per = (n_rows + threads - 1) / threads;
+  const int parts = (int)((n_rows + per - 1) / per);
+  Pool::get().run(parts, [&](int t) {
+    const int64_t lo = (int64_t)t * per, hi = lo + per < n_rows ? lo + per : n_rows;
+    run(lo, hi);
+  });
+  return 0;
+}
