@@ -492,6 +492,25 @@ def main():
            "frac_of_ceiling": e2e_value / ceiling, "affinity": affinity,
            "ingest": ("fp32 host features; pieces go raw (fp32 H2D + device rounding) or host-packed to bf16 (host cores, "
                       f"{getattr(model, 'host_pack_threads', 0)} threads), whichever route is free") if h2d != host.numel() * 4 else "fp32 H2D"}
+    # the same through the Predictor (predict.py batch): a list of per-video numpy arrays -> one native staging pass
+    # (resize + bf16 rounding into a reused pinned buffer) -> generate()'s host pipeline -> token rows -> caption strings
+    if world == 1 and not strong:
+        voc = vc.Vocabulary.from_words([f"w{i}" for i in range(V - 4)])
+        pred = vc.VideoCaptionPredictor.from_model(model, voc, config=cfg)
+        host_np = host.numpy()
+        vids = [host_np[i] for i in range(Be)]
+        pk = dict(method=wl["method"], max_length=S, **({"beam_size": K} if wl["method"] == "beam" else {}))
+        pred.predict_batch(vids, **pk)
+        torch.cuda.synchronize()
+        tp = time.perf_counter()
+        n_pred = 3
+        for _ in range(n_pred):
+            pred.predict_batch(vids, **pk)
+        torch.cuda.synchronize()
+        e2e["predictor"] = {"value": Be * n_pred / (time.perf_counter() - tp), "unit": "captions/s",
+                            "what": "VideoCaptionPredictor.predict_batch on a list of per-video fp32 numpy arrays, "
+                                    "captions decoded to strings (wall clock)"}
+        del pred, vids, host_np
     del host
 
     if rank != 0:

@@ -247,3 +247,53 @@ def test_library_staleness_is_detected_by_source_hash(tmp_path, monkeypatch):
     assert not _native.library_is_current()
     (tmp_path / "h").write_text(_native.sources_hash())
     assert _native.library_is_current()
+
+
+def test_host_stage_rows_equals_reference_resize():
+    """vc_host_stage_rows (the Predictor's batched resize/pad + optional bf16 rounding, one native pass) against the
+    oracle's restatement of predictor.py:292-315 per video: longer videos subsampled at floor(linspace), shorter ones
+    zero-padded, equal ones copied; fp32 -> fp32 exact, fp32 -> bf16 == torch's round-to-nearest-even, fp16 sources."""
+    from video_captioning_b200 import _native
+    from video_captioning_b200.predictor import resize_indices
+    rng = np.random.default_rng(0)
+    T, F = 16, 72
+    vids = [rng.standard_normal((n, F)).astype(np.float32) for n in (16, 40, 7, 1, 33, 16, 200)]
+    exp = np.stack([oracle_resize(v, T) for v in vids])
+    for src_np, src_t in ((np.float32, torch.float32), (np.float16, torch.float16)):
+        arrs = [np.ascontiguousarray(v.astype(src_np)) for v in vids]
+        rows = np.empty((len(arrs), T), dtype=np.uint64)
+        for b, a in enumerate(arrs):
+            idx = resize_indices(a.shape[0], T)
+            rows[b] = np.where(idx >= 0, a.ctypes.data + idx * (F * a.itemsize), 0).astype(np.uint64)
+        want = torch.from_numpy(np.stack([oracle_resize(a, T) for a in arrs]))
+        for dst_t in ((torch.float32, torch.bfloat16) if src_t == torch.float32 else (torch.float16, torch.bfloat16, torch.float32)):
+            for threads in (1, 5):
+                dst = torch.full((len(arrs), T, F), 7.0).to(dst_t)
+                _native.host_stage_rows(rows.reshape(-1), len(arrs) * T, F, src_t, dst, threads)
+                assert torch.equal(dst, want.to(torch.float32).to(dst_t) if dst_t != src_t else want), (src_t, dst_t, threads)
+    assert np.array_equal(exp[2][7:], np.zeros((9, F), np.float32))
+
+
+def test_result_packaging_matches_predict_py(tmp_path):
+    """save_batch_results / save_single_result / save_multiple_captions write what src/predict.py:55-71, :105-137, :174-189
+    write: the same keys, indent 2, and a captions file with an empty line for each failed video."""
+    import json
+    results = [{"video_path": "a.mp4", "caption": "a man is running", "tokens": [1, 5, 6, 2], "method": "beam"},
+               {"video_path": "b.mp4", "caption": "", "error": "Feature file not found: b.npy"},
+               {"video_path": "c.mp4", "caption": "a dog", "tokens": [7, 2], "method": "greedy",
+                "attention_weights": torch.ones(2, 4)}]
+    vc.save_batch_results(results, tmp_path / "o.json", tmp_path / "c.txt", method="beam", max_length=20, beam_size=5,
+                          length_penalty=1.0, temperature=1.0)
+    d = json.load(open(tmp_path / "o.json"))
+    assert list(d) == ["parameters", "results"]
+    assert d["parameters"] == {"method": "beam", "max_length": 20, "beam_size": 5, "length_penalty": 1.0, "temperature": 1.0}
+    assert d["results"][1]["error"].startswith("Feature file") and d["results"][2]["attention_weights"] == [[1.0] * 4] * 2
+    assert open(tmp_path / "c.txt").read() == "a man is running\n\na dog\n"
+    assert open(tmp_path / "o.json").read().startswith('{\n  "parameters": {\n    "method"')
+    vc.save_single_result(results[0], "a.mp4", tmp_path / "s.json", method="beam")
+    d = json.load(open(tmp_path / "s.json"))
+    assert list(d) == ["video_path", "caption", "method", "tokens", "parameters"] and d["tokens"] == [1, 5, 6, 2]
+    caps = [{"caption": "x", "score": 1.0 / np.float64(0.7), "tokens": [3], "temperature": np.float64(0.7)}]
+    vc.save_multiple_captions(caps, "a.mp4", tmp_path / "m.json", num_captions=1, method="greedy")
+    d = json.load(open(tmp_path / "m.json"))
+    assert list(d) == ["video_path", "captions", "parameters"] and abs(d["captions"][0]["temperature"] - 0.7) < 1e-12

@@ -9,7 +9,8 @@ from .attention import (BahdanauAttention, LuongAttention, MultiHeadAttention,  
                         create_attention_mechanism)
 from .decoder import CaptionDecoder  # noqa: F401
 from .encoder import VideoEncoder  # noqa: F401
-from .predictor import BatchPredictor, VideoCaptionPredictor  # noqa: F401
+from .predictor import (BatchPredictor, VideoCaptionPredictor, save_batch_results,  # noqa: F401
+                        save_multiple_captions, save_single_result)
 from .sharding import ShardedCaptioner, shard_bounds  # noqa: F401
 from .video_captioning_model import VideoCaptioningModel  # noqa: F401
 from .vocabulary import Vocabulary  # noqa: F401
@@ -17,5 +18,6 @@ from .vocabulary import Vocabulary  # noqa: F401
 __all__ = [
     "VideoCaptioningModel", "VideoEncoder", "CaptionDecoder", "BahdanauAttention", "LuongAttention",
     "MultiHeadAttention", "create_attention_mechanism", "VideoCaptionPredictor", "BatchPredictor", "Vocabulary",
-    "ShardedCaptioner", "shard_bounds", "build_library", "load_library", "LIB_PATH",
+    "ShardedCaptioner", "shard_bounds", "build_library", "load_library", "LIB_PATH", "save_single_result", "save_batch_results",
+    "save_multiple_captions",
 ]

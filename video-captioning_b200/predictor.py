@@ -10,15 +10,36 @@ Differences from the reference, all on purpose:
 """
 from __future__ import annotations
 
+import json
 import logging
+import os
 from pathlib import Path
 from typing import Dict, List, Optional, Union
 
 import numpy as np
 import torch
 
+from . import _native
 from .video_captioning_model import VideoCaptioningModel
 from .vocabulary import Vocabulary
+
+_LINSPACE_CACHE: Dict[tuple, np.ndarray] = {}
+
+
+def resize_indices(seq_len: int, target_length: int) -> np.ndarray:
+    """Source frame of every target frame, -1 = zero padding: the reference's `_resize_features`
+    (predictor.py:303-315; same rule in data/dataset.py:136-148) as an index vector."""
+    key = (seq_len, target_length)
+    idx = _LINSPACE_CACHE.get(key)
+    if idx is None:
+        if seq_len >= target_length:
+            idx = (np.arange(target_length, dtype=np.int64) if seq_len == target_length else
+                   torch.linspace(0, seq_len - 1, target_length, dtype=torch.long).numpy())       # :310
+        else:
+            idx = np.concatenate([np.arange(seq_len, dtype=np.int64), np.full(target_length - seq_len, -1, np.int64)])
+        if len(_LINSPACE_CACHE) < 4096:
+            _LINSPACE_CACHE[key] = idx
+    return idx
 
 
 def load_inference_package(model_path: Union[str, Path]) -> dict:
@@ -72,6 +93,9 @@ class VideoCaptionPredictor:
         self.logger = logging.getLogger(__name__)
         self.precision = precision
         self.num_heads = num_heads
+        self._stage_buf = torch.empty(0)
+        self._stage_key = None
+        self._stage_threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
         if model_path is not None:
             self._load_model(Path(model_path), config)
 
@@ -98,16 +122,52 @@ class VideoCaptionPredictor:
         self.logger.info("Loaded model with %d vocabulary size", len(self.vocabulary))
 
     # ------------------------------------------------------------------ batched core
-    def _to_device(self, features_list: List[np.ndarray]) -> torch.Tensor:
+    def _stage_host(self, features_list: List[np.ndarray]) -> torch.Tensor:
+        """The batch's ``torch.FloatTensor(features)`` + ``_resize_features`` (predictor.py:101-107, :292-315) as ONE
+        native pass (vc_host_stage_rows, all host cores): only the frames the linspace subsampling selects are read, short
+        videos are zero-padded, and the rows land in a reused pinned staging buffer -- as bf16 in bf16 mode (rounded once,
+        to nearest even, exactly what the device would do; half the bytes over the link) or as stored (fp32, or fp16
+        when the .npy files hold halves).  The pinned tensor is handed to ``model.generate``, whose host path streams it to
+        the device double-buffered and overlapped with the decode of the previous chunk."""
         T = self.config.model.video_sequence_length
-        rows = [resize_features(np.asarray(f, dtype=np.float32), T) for f in features_list]
-        host = torch.from_numpy(np.stack(rows, axis=0))
-        return host.pin_memory().to(self.device, non_blocking=True)
+        F = self.config.model.cnn_feature_dim
+        arrs = []
+        for f in features_list:
+            a = np.asarray(f)
+            if a.dtype not in (np.float32, np.float16):
+                a = a.astype(np.float32)
+            if a.ndim != 2 or a.shape[1] != F:
+                raise ValueError(f"video features must be [frames, {F}], got {a.shape}")
+            arrs.append(np.ascontiguousarray(a))
+        src_dtype = torch.float16 if all(a.dtype == np.float16 for a in arrs) else torch.float32
+        if src_dtype == torch.float32:
+            arrs = [a if a.dtype == np.float32 else a.astype(np.float32) for a in arrs]
+        dst_dtype = torch.bfloat16 if self.model.precision == "bf16" else src_dtype
+        B = len(arrs)
+        es = arrs[0].itemsize
+        rows = np.empty((B, T), dtype=np.uint64)
+        for b, a in enumerate(arrs):
+            idx = resize_indices(a.shape[0], T)
+            addr = a.ctypes.data + idx * (F * es)
+            rows[b] = np.where(idx >= 0, addr, 0).astype(np.uint64)
+        key = (dst_dtype, T, F)
+        if self._stage_key != key or self._stage_buf.shape[0] < B:
+            cap = max(B, 2 * (self._stage_buf.shape[0] if self._stage_key == key else 0))
+            self._stage_buf = torch.empty(cap, T, F, dtype=dst_dtype).pin_memory()
+            self._stage_key = key
+        host = self._stage_buf[:B]
+        _native.host_stage_rows(rows.reshape(-1), B * T, F, src_dtype, host, self._stage_threads)
+        del arrs
+        return host
+
+    def _to_device(self, features_list: List[np.ndarray]) -> torch.Tensor:
+        """Staged features on the device as fp32 [B,T,F] (teacher-forced / explain path)."""
+        return self._stage_host(features_list).to(self.device, non_blocking=True).float()
 
     def _predict_rows(self, features_list, method, max_length, beam_size, length_penalty, temperature):
         if method not in ("greedy", "beam"):
             raise ValueError(f"Unsupported generation method: {method}")
-        x = self._to_device(features_list)
+        x = self._stage_host(features_list)      # pinned host tensor: generate() runs its double-buffered ingest pipeline
         voc = self.vocabulary
         with torch.no_grad():
             if method == "greedy":
@@ -170,13 +230,35 @@ class VideoCaptionPredictor:
         return torch.cat([features, pad], dim=1)
 
     def generate_multiple_captions(self, video_features: np.ndarray, num_captions: int = 5, method: str = "beam",
-                                   max_length: int = 20, beam_size: int = 10, temperature: float = 1.0) -> List[Dict]:
-        """predictor.py:317-378: 'beam' returns ONE caption with score 1.0 from a beam of
-        max(beam_size, num_captions); 'greedy' returns num_captions runs at temperatures linspace(0.7, 1.3)."""
+                                   max_length: int = 20, beam_size: int = 10, temperature: float = 1.0,
+                                   diverse: bool = False, length_penalty: float = 1.0) -> List[Dict]:
+        """predictor.py:317-378.  Default (``diverse=False``) is the reference's behaviour: 'beam' returns ONE caption with
+        score 1.0 from a beam of max(beam_size, num_captions); 'greedy' returns num_captions runs at temperatures
+        linspace(0.7, 1.3) with score 1/temperature.
+
+        ``diverse=True`` (opt-in, beam only) is what the reference's comment at :353 asks for -- "modify beam search to
+        return multiple hypotheses": one real beam search (only beam 0 live at step 0, so the K rows are different
+        hypotheses) whose n-best list is returned with the length-normalised log-probability scores of
+        video_captioning_model.py:237-242 (completed hypotheses first, best first)."""
         if method == "beam":
             beam_size = max(beam_size, num_captions)
-            r = self.predict_from_features(video_features, method="beam", max_length=max_length, beam_size=beam_size)
-            return [{"caption": r["caption"], "score": 1.0, "tokens": r["tokens"]}]
+            if not diverse:
+                r = self.predict_from_features(video_features, method="beam", max_length=max_length, beam_size=beam_size)
+                return [{"caption": r["caption"], "score": 1.0, "tokens": r["tokens"]}]
+            voc = self.vocabulary
+            x = self._stage_host([video_features])
+            with torch.no_grad():
+                out = self.model.generate(x, voc.start_idx, voc.end_idx, max_length=max_length, method="beam",
+                                          beam_size=beam_size, length_penalty=length_penalty, diverse_beams=True,
+                                          num_return_sequences=num_captions)
+            nt, nl, ns = out["nbest_tokens"][0].cpu(), out["nbest_lengths"][0].cpu(), out["nbest_scores"][0].cpu()
+            caps = []
+            for j in range(nt.shape[0]):
+                if int(nl[j]) == 0:
+                    continue
+                row = nt[j, : int(nl[j])].tolist()
+                caps.append({"caption": voc.decode_caption(row, remove_special_tokens=True), "score": float(ns[j]), "tokens": row})
+            return caps
         caps = []
         for temp in np.linspace(0.7, 1.3, num_captions):
             r = self.predict_from_features(video_features, method="greedy", max_length=max_length, temperature=float(temp))
@@ -224,3 +306,59 @@ class BatchPredictor:
                     batch[j] = r
             results.extend(batch)
         return results
+
+
+# ---------------------------------------------------------------------- result packaging (src/predict.py)
+def _jsonable(x):
+    """Results may hold tensors / arrays (greedy results carry 'attention_weights', predictor.py:142-143; the reference's
+    own json.dump raises TypeError on them) and numpy scalars ('temperature', :375): write them as lists / numbers."""
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().tolist()
+    if isinstance(x, np.ndarray):
+        return x.tolist()
+    if isinstance(x, (np.floating, np.integer)):
+        return x.item()
+    if isinstance(x, dict):
+        return {k: _jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_jsonable(v) for v in x]
+    if isinstance(x, Path):
+        return str(x)
+    return x
+
+
+def save_single_result(result: Dict, video_path, output, method: str = "greedy", max_length: int = 20, beam_size: int = 5,
+                       length_penalty: float = 1.0, temperature: float = 1.0) -> None:
+    """predict.py single, :55-71: {'video_path', 'caption', 'method', 'tokens', 'parameters': {...}}."""
+    data = {"video_path": str(video_path) if video_path is not None else None, "caption": result["caption"],
+            "method": method, "tokens": _jsonable(result["tokens"]),
+            "parameters": {"max_length": max_length, "beam_size": beam_size, "length_penalty": length_penalty,
+                           "temperature": temperature}}
+    with open(output, "w") as f:
+        json.dump(data, f, indent=2)
+
+
+def save_batch_results(results: List[Dict], output=None, captions_file=None, method: str = "greedy", max_length: int = 20,
+                       beam_size: int = 5, length_penalty: float = 1.0, temperature: float = 1.0) -> None:
+    """predict.py batch, :105-137: JSON {'parameters': {...}, 'results': [...]} and / or a captions file with one caption
+    per line in input order and an EMPTY line for every failed video (so line i always belongs to video i)."""
+    if output:
+        data = {"parameters": {"method": method, "max_length": max_length, "beam_size": beam_size,
+                               "length_penalty": length_penalty, "temperature": temperature},
+                "results": _jsonable(results)}
+        with open(output, "w") as f:
+            json.dump(data, f, indent=2)
+    if captions_file:
+        with open(captions_file, "w") as f:
+            for r in results:
+                f.write(f"{r['caption']}\n" if "error" not in r else "\n")
+
+
+def save_multiple_captions(captions: List[Dict], video_path, output, num_captions: int = 5, method: str = "beam",
+                           max_length: int = 20, beam_size: int = 5, temperature: float = 1.0) -> None:
+    """predict.py multiple, :174-189: {'video_path', 'captions': [...], 'parameters': {...}}."""
+    data = {"video_path": str(video_path) if video_path is not None else None, "captions": _jsonable(captions),
+            "parameters": {"num_captions": num_captions, "method": method, "max_length": max_length, "beam_size": beam_size,
+                           "temperature": temperature}}
+    with open(output, "w") as f:
+        json.dump(data, f, indent=2)

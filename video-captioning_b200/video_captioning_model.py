@@ -207,7 +207,11 @@ class VideoCaptioningModel(nn.Module):
                                        temperature=kwargs.get("temperature", 1.0), diverse=kwargs.get("diverse_beams", False),
                                        nbest=nbest)
         if video_features.device.type == "cpu":
-            can_pack = self.precision == "bf16" and video_features.dtype == torch.float32 and video_features.dim() == 3
+            if video_features.dim() != 3 or video_features.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+                raise ValueError("host video_features must be a float32 / float16 / bfloat16 [B,T,F] tensor")
+            if video_features.dtype == torch.bfloat16 and self.precision != "bf16":
+                raise ValueError("bfloat16 host features need precision='bf16'")
+            can_pack = self.precision == "bf16" and video_features.dtype == torch.float32
             if can_pack:
                 # bf16 mode always goes through the piece pipeline (every feature rounded once to bf16, so the result does
                 # not depend on the route); host_pack only decides whether host cores take part
@@ -243,17 +247,19 @@ class VideoCaptioningModel(nn.Module):
         streamed to the device in chunks on a copy stream, double-buffered, so the PCIe transfer of chunk
         i+1 overlaps the compute of chunk i.  Pass pinned memory (``tensor.pin_memory()``) for full speed.
         The arithmetic still runs only on the GPU."""
-        if feats.dtype != torch.float32 or feats.dim() != 3:
-            raise ValueError("host video_features must be a float32 [B,T,F] tensor")
+        # fp32 features cross the link as they are; features stored as halves (float16 .npy files load that way, the
+        # reference's np.load -> tensor path is dtype-agnostic, predictor.py:101-102) or already rounded to bf16
+        # (VideoCaptionPredictor's staging in bf16 mode) cross at half the bytes and are widened / rounded on the device
         dev = h.device
+        want = torch.bfloat16 if self.precision == "bf16" and feats.dtype != torch.float32 else torch.float32
         B, T, F = feats.shape
         chunk = max(1, min(self.host_chunk_size, self.chunk_size, B))
         compute = torch.cuda.current_stream(dev)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
-        key = (chunk, T, F, str(dev))
+        key = (chunk, T, F, str(dev), feats.dtype)
         if self._staging_key != key:
-            self._staging = [torch.empty(chunk, T, F, dtype=torch.float32, device=dev) for _ in range(2)]
+            self._staging = [torch.empty(chunk, T, F, dtype=feats.dtype, device=dev) for _ in range(2)]
             self._staging_key = key
         ready = [torch.cuda.Event() for _ in range(2)]
         free = [torch.cuda.Event() for _ in range(2)]
@@ -276,7 +282,10 @@ class VideoCaptioningModel(nn.Module):
                 enqueue_copy(i + 1)
             compute.wait_event(ready[i % 2])
             mk = None if mask is None else mask[lo:hi].to(dev, non_blocking=True)
-            outs.append(gen(self._staging[i % 2][: hi - lo], mk))
+            x = self._staging[i % 2][: hi - lo]
+            if x.dtype != want:
+                x = x.to(want)          # fp16 -> fp32 (exact) or fp16 -> bf16 (the rounding bf16 mode applies anyway)
+            outs.append(gen(x, mk))
             free[i % 2].record(compute)
         return outs
 
