@@ -84,6 +84,25 @@ def _attention_kind_of(state_dict) -> str:
     return "luong_dot"
 
 
+class _ListSource:
+    """A batch given as per-video [T',F] arrays, presented to VideoCaptioningModel.generate as a source of bf16 pieces."""
+
+    def __init__(self, arrs: List[np.ndarray], T: int, F: int, threads: int):
+        self.arrs, self.T, self.F, self.threads = arrs, T, F, threads
+        self.shape = (len(arrs), T, F)
+        self.src_dtype = torch.float16 if arrs[0].dtype == np.float16 else torch.float32
+        self.dim = lambda: 3
+
+    def pack_piece(self, lo: int, hi: int, dst: torch.Tensor) -> None:
+        T, F = self.T, self.F
+        rows = np.empty((hi - lo, T), dtype=np.uint64)
+        for i in range(lo, hi):
+            a = self.arrs[i]
+            idx = resize_indices(a.shape[0], T)
+            rows[i - lo] = np.where(idx >= 0, a.ctypes.data + idx * (F * a.itemsize), 0).astype(np.uint64)
+        _native.host_stage_rows(rows.reshape(-1), (hi - lo) * T, F, self.src_dtype, dst, self.threads)
+
+
 class VideoCaptionPredictor:
     def __init__(self, model_path: Optional[Path] = None, device: Optional[torch.device] = None, config=None,
                  precision: str = "fp32", num_heads: int = 8):
@@ -160,6 +179,24 @@ class VideoCaptionPredictor:
         del arrs
         return host
 
+    def _piece_source(self, features_list: List[np.ndarray]):
+        """bf16 mode: instead of staging the whole batch before the first byte crosses the link, hand generate() a piece
+        source -- its packer thread resizes + rounds pieces of ``host_piece_size`` videos into pinned bf16 buffers
+        (vc_host_stage_rows) while earlier pieces are in flight and earlier chunks are being decoded."""
+        T = self.config.model.video_sequence_length
+        F = self.config.model.cnn_feature_dim
+        arrs = []
+        for f in features_list:
+            a = np.asarray(f)
+            if a.dtype not in (np.float32, np.float16):
+                a = a.astype(np.float32)
+            if a.ndim != 2 or a.shape[1] != F:
+                raise ValueError(f"video features must be [frames, {F}], got {a.shape}")
+            arrs.append(np.ascontiguousarray(a))
+        if not all(a.dtype == arrs[0].dtype for a in arrs):
+            arrs = [a if a.dtype == np.float32 else a.astype(np.float32) for a in arrs]
+        return _ListSource(arrs, T, F, self._stage_threads)
+
     def _to_device(self, features_list: List[np.ndarray]) -> torch.Tensor:
         """Staged features on the device as fp32 [B,T,F] (teacher-forced / explain path)."""
         return self._stage_host(features_list).to(self.device, non_blocking=True).float()
@@ -167,7 +204,10 @@ class VideoCaptionPredictor:
     def _predict_rows(self, features_list, method, max_length, beam_size, length_penalty, temperature):
         if method not in ("greedy", "beam"):
             raise ValueError(f"Unsupported generation method: {method}")
-        x = self._stage_host(features_list)      # pinned host tensor: generate() runs its double-buffered ingest pipeline
+        if self.model.precision == "bf16" and len(features_list) >= 2 * self.model.host_piece_size:
+            x = self._piece_source(features_list)      # staged piece by piece inside generate()'s ingest pipeline
+        else:
+            x = self._stage_host(features_list)        # pinned host tensor: generate() runs its double-buffered ingest
         voc = self.vocabulary
         with torch.no_grad():
             if method == "greedy":

@@ -206,7 +206,11 @@ class VideoCaptioningModel(nn.Module):
                                        beam_size=kwargs.get("beam_size", 5), length_penalty=kwargs.get("length_penalty", 1.0),
                                        temperature=kwargs.get("temperature", 1.0), diverse=kwargs.get("diverse_beams", False),
                                        nbest=nbest)
-        if video_features.device.type == "cpu":
+        if hasattr(video_features, "pack_piece"):     # a host piece source (VideoCaptionPredictor), bf16 mode
+            if self.precision != "bf16":
+                raise ValueError("host piece sources need precision='bf16'")
+            outs = self._generate_from_host_packed(h, None, video_mask, gen, pack=True, source=video_features)
+        elif video_features.device.type == "cpu":
             if video_features.dim() != 3 or video_features.dtype not in (torch.float32, torch.float16, torch.bfloat16):
                 raise ValueError("host video_features must be a float32 / float16 / bfloat16 [B,T,F] tensor")
             if video_features.dtype == torch.bfloat16 and self.precision != "bf16":
@@ -289,7 +293,7 @@ class VideoCaptioningModel(nn.Module):
             free[i % 2].record(compute)
         return outs
 
-    def _generate_from_host_packed(self, h, feats: torch.Tensor, mask, gen, pack: bool = True):
+    def _generate_from_host_packed(self, h, feats, mask, gen, pack: bool = True, source=None):
         """bf16-mode ingest of HOST fp32 features.  The PCIe link (54 GB/s, 1.3 MB per video) is the end-to-end
         bottleneck and bf16 mode rounds the features to bf16 anyway, so the batch is cut into pieces of
         ``host_piece_size`` videos that reach the device by one of two routes, whichever is free:
@@ -299,9 +303,14 @@ class VideoCaptioningModel(nn.Module):
         Within a chunk of ``host_chunk_size`` videos the copy loop takes raw pieces from the front and the packer takes
         pieces from the back until they meet; every piece lands in one device bf16 buffer and the chunk is decoded as
         soon as its pieces are in (vc_generate_ex, VC_DTYPE_BF16), while the next chunk is on its way.  All features are rounded exactly once, to nearest even, on
-        either route, so results do not depend on the split.  Rows are returned in input order."""
+        either route, so results do not depend on the split.  Rows are returned in input order.
+
+        ``source`` (instead of ``feats``): an object with ``shape`` = (B,T,F) and ``pack_piece(lo, hi, dst_bf16)`` that
+        writes videos [lo,hi) rounded to bf16 into a pinned buffer -- the Predictor's list of per-video arrays, resized and
+        rounded by vc_host_stage_rows piece by piece.  Every piece then takes the packed route (there is no contiguous
+        fp32 batch to send raw), still overlapped with the copies and the decode of the previous chunk."""
         dev = h.device
-        B, T, F = feats.shape
+        B, T, F = source.shape if source is not None else feats.shape
         piece = max(1, min(self.host_piece_size, self.chunk_size, B))
         window = min(B, max(piece, min(self.chunk_size, self.host_window_size) // piece * piece))
         compute = torch.cuda.current_stream(dev)
@@ -316,7 +325,7 @@ class VideoCaptioningModel(nn.Module):
                 host16=[torch.empty(piece, T, F, dtype=torch.bfloat16).pin_memory() for _ in range(4)])
             self._packed_key = key
         st = self._packed
-        pinned = feats.is_pinned()
+        pinned = feats.is_pinned() if source is None else False
         outs = {}
         chunk_free = {}                      # chunk slot of the window -> event: its last decode has read dev16
         raw_free = [None, None]
@@ -371,7 +380,10 @@ class VideoCaptioningModel(nn.Module):
                             ev.synchronize()
                         lo, hi = pieces[idx]
                         t0 = time.perf_counter()
-                        _native.host_pack_bf16(feats[lo:hi], buf[: hi - lo], self.host_pack_threads)
+                        if source is not None:
+                            source.pack_piece(lo, hi, buf[: hi - lo])
+                        else:
+                            _native.host_pack_bf16(feats[lo:hi], buf[: hi - lo], self.host_pack_threads)
                         stats["pack_s"] += time.perf_counter() - t0
                         stats["packed"] += 1
                         with lock:
@@ -397,7 +409,7 @@ class VideoCaptioningModel(nn.Module):
                 with lock:
                     if ready:
                         item = ("packed",) + ready.popleft()
-                    else:
+                    elif source is None:
                         idx = claim(False)
                         if idx is not None:
                             item = ("raw", idx, None)
