@@ -181,7 +181,7 @@ int vc_linear(int32_t precision, const float* A, const float* W, const float* bi
 
 /* One attention step (attention.py forward of the model's variant) for R = B*K rows:
  * enc_out [B,T,H], hidden [R,H] (top-layer h of the previous step), mask [B,T] or NULL ->
- * context [R,H], weights [R,T]. */
+ * context [R,H], weights [R,T] (weights may be NULL: the context-only kernels of the decode loop are taken). */
 int vc_attention_step(vc_model_t* m, const float* enc_out, const float* hidden, const float* mask, int32_t B, int32_t T,
                       int32_t K, float* context, float* weights, void* workspace, size_t workspace_bytes,
                       vc_stream_t stream);

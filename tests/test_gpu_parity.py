@@ -265,6 +265,41 @@ def test_fp32_greedy_vs_oracle_config1():
     assert np.abs(out["attention_weights"].cpu().numpy()[:, 0] - ref["attention_weights"].numpy()[:, 0]).max() < 1e-4
 
 
+@pytest.mark.parametrize("att,shape,B,K", [("luong_dot", "c3", 310, 5), ("luong_general", "c3", 7, 3), ("luong_general", "msvd", 300, 8),
+                                          ("luong_dot", "small", 5, 1), ("multihead", "c4", 310, 3), ("multihead", "small", 9, 5),
+                                          ("multihead", "c3", 6, 2), ("luong_dot", "tiny", 3, 4)])
+def test_dot_attention_ring_kernel(monkeypatch, att, shape, B, K):
+    """The streaming dot-product attention kernel (attention_dot.cuh: Luong dot / general, multi-head; the context-only call of
+    the decode loop) against the oracle on sampled videos and against the generic kernel on all rows: several videos per
+    CTA, ragged masks, T not a multiple of the 16-frame tile, H = 128 ... 1024."""
+    from oracle import synth
+    cfg = synth.make_config(shape)
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, att, seed=43)
+    o = make_oracle(sd)
+    T, H = cfg.model.video_sequence_length, cfg.model.encoder_hidden_dim
+    g = torch.Generator().manual_seed(B * 131 + K)
+    enc = torch.randn(B, T, H, generator=g)
+    hid = torch.randn(B * K, H, generator=g) * (6.0 / H ** 0.5)      # score spread of a few units: neither flat nor one-hot
+    mask = torch.ones(B, T)
+    mask[B // 2, T - 5:] = 0
+    mask[B - 1, : T // 3] = 0
+    rows = sorted({0, B // 2, B - 1})
+    sel = torch.tensor([r * K + k for r in rows for k in range(K)])
+    ctx_o, _ = o.attend(enc[rows].repeat_interleave(K, 0), hid[sel], mask[rows].repeat_interleave(K, 0))
+    m = make_native_model(cfg, V, sd, att, "bf16")
+    h = m._handle()
+    for msk in (mask.cuda(), None):
+        ctx, w = h.attention_step(enc.cuda(), hid.cuda(), msk, K, want_weights=False)
+        assert w is None
+        monkeypatch.setenv("VC_DISABLE_ATTN_DOT", "1")
+        ctx_g, _ = h.attention_step(enc.cuda(), hid.cuda(), msk, K, want_weights=False)
+        monkeypatch.delenv("VC_DISABLE_ATTN_DOT")
+        assert rel_err(ctx.cpu(), ctx_g.cpu()) < 1e-2
+        if msk is not None:
+            assert rel_err(ctx[sel].cpu(), ctx_o) < BF16_LOGIT_TOL
+
+
 def test_luong_h1024_config3_small_batch():
     """Config 3 shape (H=1024, Luong general/dot) at B=4 vs the oracle, fp32 tokens + bf16 logits."""
     from oracle import synth

@@ -403,7 +403,9 @@ class NativeModel:
                                               _stream(self.device)), "vc_forward_teacher")
         return logits, attn, enc_out
 
-    def attention_step(self, enc_out, hidden, mask, K):
+    def attention_step(self, enc_out, hidden, mask, K, want_weights=True):
+        """One attention step.  ``want_weights=False`` returns (context, None) through the context-only kernels the
+        decode loop uses (the weights are an extra output of explain_prediction / teacher forcing)."""
         require_cuda(enc_out, "enc_out")
         e = enc_out.detach().float().contiguous()
         h = hidden.detach().float().contiguous()
@@ -411,7 +413,7 @@ class NativeModel:
         R = B * K
         m = None if mask is None else mask.detach().float().contiguous()
         ctx = torch.empty(R, H, dtype=torch.float32, device=self.device)
-        w = torch.empty(R, T, dtype=torch.float32, device=self.device)
+        w = torch.empty(R, T, dtype=torch.float32, device=self.device) if want_weights else None
         with torch.cuda.device(self.device):
             ws = self._workspace(B, T, K, 1)
             check(self.lib.vc_attention_step(self._h, _ptr(e), _ptr(h), _ptr(m), B, T, K, _ptr(ctx), _ptr(w), _ptr(ws),

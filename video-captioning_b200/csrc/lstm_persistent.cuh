@@ -5,8 +5,10 @@
 //
 //   grid  = (4H/128 gate-column tiles) x (ceil(B/256) row tiles) x (2 directions)   <= #SMs, 1 CTA / SM
 //   smem  = W_hh tile [128 x H] bf16, RESIDENT for the whole layer (128 KB at H=512)
-//           + 3-stage ring of h_{t-1} k-blocks (TMA), + the step's input-projection tile (TMA),
-//           + h staging boxes for the TMA stores
+//           + 3-stage ring of h_{t-1} k-blocks (TMA) + h staging boxes for the TMA stores.
+//           The input-projection tile does NOT go through shared memory: each epilogue thread loads its own 128
+//           contiguous bytes (one row x 16 hidden units x 4 gates) into registers before it waits for the step's
+//           accumulator, i.e. under the step's own load + MMA time.
 //   TMEM  = two 128x128 fp32 accumulators (rows 0-127 / 128-255 of the CTA's row tile): the LSTM epilogue
 //           of one half overlaps the tcgen05 main loop of the other
 //   regs  = the cell state c (one row x 32 hidden units per epilogue thread) never leaves registers
@@ -18,10 +20,16 @@
 // producers before they load h_t for step t+1.  The spin is safe because the launch is cooperative
 // (all CTAs co-resident) and bounded (trap instead of hang).
 //
+// Where a step's 7.2 us go (clock64 stamps of one CTA, scripts/plstm_probe.cu, VC_PLSTM_PROBE): flag seen -> first k-block
+// in shared memory 0.9 us, -> all 8 k-blocks through the 3-slot ring and their MMAs committed 3.3 us, cell epilogue 1.0 us,
+// bulk store of the h slice 0.4 us, release + flag visible to the 16 consumers 1.5 us.  The two row-halves of a CTA are two
+// such chains half a period apart.  A 16-CTA cluster variant (remote mbarrier arrivals instead of the L2 flag, every k-block
+// multicast to the cluster: 2 MB instead of 32 MB of L2 reads per step) measured the same chain length -- a slot can only be
+// refilled when all 16 CTAs have consumed it -- and only 7 clusters of 16 fit a B200, so it was not kept.
+//
 // Warp roles (608 threads): w0 = h_{t-1} TMA producer, w1 = TMEM alloc + MMA issuer, w2-9 = epilogue of
 // row-half 0, w10-17 = epilogue of row-half 1 (two warps per TMEM lane quarter, each taking 16 of the tile's 32 hidden
-// units: the epilogue is on the step's critical path, so its latency matters more than its issue slots),
-// w18 = input-projection TMA producer.
+// units: the epilogue is on the step's critical path, so its latency matters more than its issue slots).
 #pragma once
 #include <cooperative_groups.h>
 
@@ -30,8 +38,11 @@
 namespace vc {
 namespace tc {
 
-constexpr int kPlThreads = 608;
+constexpr int kPlThreads = 576;
 constexpr int kPlEpiThreads = 256;  // epilogue threads per row-half
+// Ring depth.  Measured with scripts/plstm_probe.cu (B = 1024, T = 80, H = 512, us per step): 3 stages 7.58, 4 stages 8.71,
+// 5 stages 8.79.  All 16 CTAs of a group pull the same 16 KB boxes of h_{t-1} from L2 at the same moment; more boxes in flight
+// only lengthen the latency of the first one (0.9 -> 1.5 us) and of everything else that goes through L2.
 constexpr int kPlStages = 3;
 constexpr int kPlBN = 128;          // gate columns per CTA = 32 hidden units
 
@@ -39,14 +50,20 @@ struct alignas(64) PLstmMaps {
   CUtensorMap out_ld;   // layer output [B, T*2H] bf16, box 64 x 128, 128B swizzle (h_{t-1} loads)
   CUtensorMap out_st;   // same buffer, box 32 x 128, 64B swizzle (h_t stores)
   CUtensorMap W[2];     // W_hh [4H, H] per direction, box 64 x 128
-  CUtensorMap xp;       // input projections [B, T*8H] bf16, box 64 x 128
 };
 struct PLstmArgs {
   int B, T, H;
   const float* bias[2];      // nullable (the encoder's biases are folded into xp)
+  const bf16* xp;            // input projections [B, T*8H] bf16 (both directions, gate-interleaved)
   unsigned int* flags;       // [2 dirs][MT][2 halves] arrival counters, zeroed before launch
+  long long* dbg;            // VC_PLSTM_PROBE builds (scripts/plstm_probe.cu): clock64 stamps of CTA (0,0,0), steps 40..47
 };
 
+#ifdef VC_PLSTM_PROBE
+#define PL_PROBE(ev, t) do { if (g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t) >= 40 && (t) < 48) g.dbg[((t) - 40) * 32 + (ev)] = clock64(); } while (0)
+#else
+#define PL_PROBE(ev, t) do { } while (0)
+#endif
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -71,12 +88,9 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
   const int nkb = H / BK;
   uint8_t* w_s = smem;                                    // nkb boxes of [128 n x 64 k] bf16
   uint8_t* a_s = w_s + (size_t)nkb * kBoxBytes;           // kPlStages boxes of [128 rows x 64 k]
-  uint8_t* xp_s = a_s + (size_t)kPlStages * kBoxBytes;    // 2 boxes [128 rows x 64 cols] of one row-half
-  uint8_t* h_s = xp_s + 2 * kBoxBytes;                    // 2 x [128 rows x 32 units] bf16 (64B rows)
+  uint8_t* h_s = a_s + (size_t)kPlStages * kBoxBytes;     // 2 x [128 rows x 32 units] bf16 (64B rows)
   __shared__ __align__(8) uint64_t w_bar, full_bar[kPlStages], empty_bar[kPlStages];
-  // the input-projection buffer is shared by the two row-halves, but each half has its OWN full/empty
-  // barrier pair: with one shared pair a consumer can find the barrier two phases ahead (parity aliasing)
-  __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2], xp_full[2], xp_empty[2];
+  __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[kPlBN];
 
@@ -96,8 +110,6 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
     for (int h = 0; h < 2; ++h) {
       mbar_init(smem_u32(&tmem_full[h]), 1);
       mbar_init(smem_u32(&tmem_empty[h]), kPlEpiThreads);
-      mbar_init(smem_u32(&xp_full[h]), 1);
-      mbar_init(smem_u32(&xp_empty[h]), kPlEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -131,6 +143,7 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
               __trap();
             }
           }
+          PL_PROBE(0 + half, t);
           asm volatile("fence.proxy.async;" ::: "memory");   // order the acquire before the async-proxy loads
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -139,23 +152,7 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
             tma_load_2d(smem_u32(a_s + (size_t)stage * kBoxBytes), &maps.out_ld, fb, col0 + kb * BK, m0 + half * 128);
             if (++stage == kPlStages) { stage = 0; phase ^= 1; }
           }
-        }
-      }
-    }
-  } else if (warp == 18) {
-    if (lane == 0) {
-      // ===== input-projection tile of (step, row-half) =====
-      for (int t = 0; t < T; ++t) {
-        const int tt = (z == 0) ? t : (T - 1 - t);
-        for (int half = 0; half < 2; ++half) {
-          // the buffer is free once the previous tile -- (t, half 0) or (t-1, half 1) -- has been consumed
-          if (half == 1) mbar_wait(smem_u32(&xp_empty[0]), (uint32_t)(t & 1));
-          else if (t > 0) mbar_wait(smem_u32(&xp_empty[1]), (uint32_t)((t - 1) & 1));
-          const uint32_t xb = smem_u32(&xp_full[half]);
-          mbar_expect_tx(xb, 2 * kBoxBytes);
-          const int col = tt * 8 * H + z * 4 * H + n0;
-          tma_load_2d(smem_u32(xp_s), &maps.xp, xb, col, m0 + half * 128);
-          tma_load_2d(smem_u32(xp_s + kBoxBytes), &maps.xp, xb, col + 64, m0 + half * 128);
+          PL_PROBE(2 + half, t);
         }
       }
     }
@@ -172,6 +169,7 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
           const uint32_t d = tmem_base + (uint32_t)(half * 128);
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(smem_u32(&full_bar[stage]), phase);
+            if (kb == 0) PL_PROBE(4 + half, t);
             tc_fence_after();
             const uint64_t da = make_smem_desc(smem_u32(a_s + (size_t)stage * kBoxBytes));
             const uint64_t db = make_smem_desc(smem_u32(w_s + (size_t)kb * kBoxBytes));
@@ -182,6 +180,7 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
             if (++stage == kPlStages) { stage = 0; phase ^= 1; }
           }
           umma_commit(smem_u32(&tmem_full[half]));
+          PL_PROBE(6 + half, t);
         }
       }
     }
@@ -194,16 +193,36 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
     const int et = (warp - 2 - half * 8) * 32 + lane;     // 0..255 inside the half
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
     const uint32_t hbox = smem_u32(h_s + (size_t)half * (128 * 64));
-    const uint32_t xs = smem_u32(xp_s);
+    // this thread's input-projection row: 128 contiguous bytes per step (16 hidden units x 4 gates, gate-interleaved)
+    const int grow = m0 + half * 128 + r;
+    const bool row_ok = grow < g.B;
+    const bf16* xrow = g.xp + (size_t)(row_ok ? grow : 0) * ((size_t)T * 8 * H) + (size_t)z * 4 * H + n0 + sub * 64;
     float c[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) c[u] = 0.f;
     for (int t = 0; t < T; ++t) {
       const int tt = (z == 0) ? t : (T - 1 - t);
-      mbar_wait(smem_u32(&xp_full[half]), (uint32_t)(t & 1));
+      // issued before the wait for the accumulator: the loads complete under the step's MMA time
+      uint32_t xw[32];
+      {
+        const bf16* xp_t = xrow + (size_t)tt * 8 * H;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (row_ok) {
+            asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(xw[8 * i + 0]), "=r"(xw[8 * i + 1]), "=r"(xw[8 * i + 2]), "=r"(xw[8 * i + 3]), "=r"(xw[8 * i + 4]),
+                           "=r"(xw[8 * i + 5]), "=r"(xw[8 * i + 6]), "=r"(xw[8 * i + 7])
+                         : "l"(xp_t + 16 * i));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xw[8 * i + j] = 0u;
+          }
+        }
+      }
       if (t > 0) {
         mbar_wait(smem_u32(&tmem_full[half]), (uint32_t)((t - 1) & 1));
         tc_fence_after();
+        if (et == 0) PL_PROBE(8 + half, t);
       }
 #pragma unroll
       for (int cj = 0; cj < 2; ++cj) {
@@ -218,17 +237,10 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
         }
         float gte[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) gte[i] = __uint_as_float(v[i]) + bias_s[ci * 32 + i];
-        const uint32_t abox = xs + (uint32_t)(ci >> 1) * kBoxBytes;
-        const int ch0 = (ci & 1) * 4;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint32_t w0, w1, w2, w3;
-          lds128(swz(abox, r, ch0 + k), w0, w1, w2, w3);
-          gte[8 * k + 0] += bf16_lo(w0); gte[8 * k + 1] += bf16_hi(w0);
-          gte[8 * k + 2] += bf16_lo(w1); gte[8 * k + 3] += bf16_hi(w1);
-          gte[8 * k + 4] += bf16_lo(w2); gte[8 * k + 5] += bf16_hi(w2);
-          gte[8 * k + 6] += bf16_lo(w3); gte[8 * k + 7] += bf16_hi(w3);
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t w = xw[cj * 16 + i];
+          gte[2 * i] = __uint_as_float(v[2 * i]) + bias_s[ci * 32 + 2 * i] + bf16_lo(w);
+          gte[2 * i + 1] = __uint_as_float(v[2 * i + 1]) + bias_s[ci * 32 + 2 * i + 1] + bf16_hi(w);
         }
         float hn[8];
 #pragma unroll
@@ -248,20 +260,23 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
         tc_fence_before();
         mbar_arrive(smem_u32(&tmem_empty[half]));         // accumulator may be overwritten by step t+1
       }
-      mbar_arrive(smem_u32(&xp_empty[half]));             // input-projection tile consumed
       fence_proxy_async_smem();
+      if (et == 0) PL_PROBE(10 + half, t);
       asm volatile("bar.sync %0, 256;" ::"r"(2 + half) : "memory");
       if (et == 0) {
         tma_store_2d(&maps.out_st, hbox, tt * 2 * H + z * H + n0 / 4, m0 + half * 128);
         tma_store_commit();
         tma_store_wait_read();                            // staging box may be rewritten
+        PL_PROBE(12 + half, t);
       }
       asm volatile("bar.sync %0, 256;" ::"r"(2 + half) : "memory");
       if (et == 0) {
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // h_t slice is in global memory
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __threadfence();
+        PL_PROBE(14 + half, t);
+        // The bulk store has completed (its writes are visible to this thread); the gpu-scope release orders them before the
+        // increment.  (A fence.proxy.async + __threadfence() in front of it cost 0.35 us per step and half: 7.53 -> 7.19 us.)
         red_release_gpu_add(flag0 + half, 1u);
+        PL_PROBE(16 + half, t);
       }
     }
   }
@@ -295,7 +310,7 @@ inline int get_map_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 }
 
 inline size_t plstm_smem_bytes(int H) {
-  return (size_t)(H / BK) * kBoxBytes + (size_t)kPlStages * kBoxBytes + 2 * kBoxBytes + 2 * (128 * 64) + 1024;
+  return (size_t)(H / BK) * kBoxBytes + (size_t)kPlStages * kBoxBytes + 2 * (128 * 64) + 1024;
 }
 
 // Largest batch one cooperative launch can take (0 = shape not supported by the persistent kernel).
@@ -309,22 +324,23 @@ inline int plstm_max_batch(int H, int num_sms) {
 // One bidirectional layer, all T steps.  out: [B, T, 2H] bf16 (written), xp: [B, T, 8H] bf16 (both directions'
 // input projections incl. biases, gate-interleaved), W[dir]: [4H, H] bf16 gate-interleaved, flags: >= 4*MT uints.
 inline int launch_lstm_layer_persistent(bf16* out, const bf16* xp, const void* W0, const void* W1, int B, int T, int H,
-                                        unsigned int* flags, cudaStream_t stream) {
+                                        unsigned int* flags, cudaStream_t stream, long long* dbg = nullptr) {
   PLstmMaps mp;
   VC_TRY(get_map(&mp.out_ld, out, (uint64_t)B, (uint64_t)T * 2 * H, (uint64_t)T * 2 * H, BM, 2));
   VC_TRY(get_map_sw(&mp.out_st, out, (uint64_t)B, (uint64_t)T * 2 * H, (uint64_t)T * 2 * H, 128, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   VC_TRY(get_map(&mp.W[0], W0, (uint64_t)4 * H, (uint64_t)H, (uint64_t)H, 128, 2));
   VC_TRY(get_map(&mp.W[1], W1, (uint64_t)4 * H, (uint64_t)H, (uint64_t)H, 128, 2));
-  VC_TRY(get_map(&mp.xp, xp, (uint64_t)B, (uint64_t)T * 8 * H, (uint64_t)T * 8 * H, BM, 2));
   PLstmArgs a;
   a.B = B; a.T = T; a.H = H;
   a.bias[0] = a.bias[1] = nullptr;
+  a.xp = xp;
   a.flags = flags;
+  a.dbg = dbg;
   const int NT = 4 * H / kPlBN, MT = (B + 255) / 256;
+  dim3 grid(NT, MT, 2);
   VC_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * (size_t)4 * MT, stream));
   const size_t smem = plstm_smem_bytes(H);
   VC_CUDA(cudaFuncSetAttribute(lstm_layer_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(NT, MT, 2);
   void* args[] = {(void*)&mp, (void*)&a};
   VC_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_layer_persistent_kernel, grid, dim3(kPlThreads), args, smem, stream));
   return VC_OK;
