@@ -10,7 +10,7 @@
 //   * one producer warp keeps a ring of (video, 16-frame tile) slots full with cp.async.bulk row copies (mbarrier tx),
 //     as far ahead as the ring allows -- the first ring pass is issued before the dependency wait (PDL);
 //   * eight consumer warps take the tiles in order.  Scores: S[16 frames x 8 beams] = tile[16 x H] . q^T on mma.sync
-//     (A = ldmatrix of the tile, B = the video's queries kept in registers as bf16 hi + lo fragments: fp32-grade queries);
+//     (A = ldmatrix of the tile, B = the video's bf16 queries kept in registers as fragments);
 //     online softmax over the tiles (running max / sum, flash-attention style rescaling); context:
 //     ctx^T[H x 8 beams] += tile^T . p on mma.sync (A = ldmatrix.trans of the same tile -- or of the V tile --, B = the
 //     probabilities as bf16 hi + lo).  Every tile byte is read from shared memory twice and from HBM once.
@@ -27,19 +27,21 @@ namespace vc {
 struct AttnDotArgs {
   const bf16* skeys;     // [B, T, H] scoring operand (Luong: enc_out; multi-head: K)
   const bf16* values;    // [B, T, H] value operand (Luong: enc_out = skeys; multi-head: V)
-  const float* q;        // [R, H] fp32 projected queries (general / multi-head), or nullptr
-  const bf16* q_act;     // [R, *] hidden state used as the query (Luong dot), row stride q_ld
-  int64_t q_ld;
+  const bf16* q_act;     // [R, *] bf16 queries, row stride q_ld: the hidden state itself (Luong dot) or the projected query as
+  int64_t q_ld;          // the projection GEMM's epilogue rounds it (general / multi-head; like every activation of the bf16 mode)
   const float* mask;     // [B, T] (0 -> masked) or nullptr
   bf16* ctx;             // [R, ctx_ld]
   int64_t ctx_ld;
   int B, K, T, H, heads;
-  float scale;           // multi-head: 1/sqrt(d); folded into the query fragments
+  float scale;           // multi-head: 1/sqrt(d), applied to the scores
   int nslots;            // ring slots (host: launch_attn_dot_ws)
 };
 
-constexpr int kDotCW = 8;                         // consumer warps (latency-bound per warp: ncu showed 'wait' stalls with four)
-constexpr int kDotThreads = 32 * (kDotCW + 1);    // + 1 producer warp
+// Consumer warps per CTA (+ 1 producer warp).  The consumers are latency-bound (dependent ldmatrix -> mma chains, one softmax
+// round and one named barrier per tile): measured with scripts/attn_dot_probe.cu, compute alone, B = 1024, T = 80:
+// H = 1024: 4 warps x 16 m-tiles 70 us, 8 warps x 8 m-tiles 102 us (96-register cap at two CTAs per SM: spills);
+// H = 512: 8 warps x 4 m-tiles 40 us.  The producer / HBM side alone delivers 4.6-4.9 TB/s (36 us at H = 1024).
+inline int attn_dot_warps(int H) { return H > 512 ? 4 : 8; }
 constexpr int kDotMaxSlots = 6;
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -47,22 +49,20 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
 }
 // coherent loads of data written by the previous kernel of the stream (read after pdl_wait)
-__device__ __forceinline__ float2 ld_f2(const float* p) {
-  float2 r;
-  asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
-  return r;
-}
 __device__ __forceinline__ uint32_t ld_u32(const void* p) {
   uint32_t r;
   asm volatile("ld.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
   return r;
 }
 
-// MAXMT: m-tiles (= k-steps) of 16 per warp, H <= 16 * kDotCW * MAXMT.  HPW: heads per warp (0: single head, partial scores
-// summed across the warps; > 0: H == 16 * kDotCW * MAXMT exactly, head dim = 16 * MAXMT / HPW).  SEPV: separate value tile (multi-head).
-template <int MAXMT, int HPW, bool SEPV>
-__global__ void __launch_bounds__(kDotThreads, 2) attn_dot_ws_kernel(const AttnDotArgs a) {
-  extern __shared__ __align__(128) uint8_t smem_u8[];
+// CW: consumer warps.  MAXMT: m-tiles (= k-steps) of 16 per warp, H == 16 * CW * MAXMT.  HPW: heads per warp (0: single head,
+// partial scores summed across the warps, values = skeys; > 0: multi-head with a separate value tile, head dim = 16 * MAXMT / HPW).
+template <int CW, int MAXMT, int HPW>
+__global__ void __launch_bounds__(32 * (CW + 1), 2) attn_dot_ws_kernel(const AttnDotArgs a) {
+  constexpr int kDotCW = CW;
+  constexpr bool SEPV = HPW > 0;
+  constexpr int nmt = MAXMT;                       // m-tiles = k-steps of a warp
+  extern __shared__ __align__(16) uint8_t smem_u8[];
   constexpr int HP = HPW > 0 ? HPW : 1;            // softmax states per warp
   constexpr int NKH = MAXMT / HP;                  // m-tiles / k-steps per head (HPW > 0)
   constexpr float kL2e = 1.4426950408889634f;
@@ -95,6 +95,10 @@ __global__ void __launch_bounds__(kDotThreads, 2) attn_dot_ws_kernel(const AttnD
     if (lane == 0) {
       auto issue = [&](int vi, int ft, int slot) {
         const uint32_t fb = full + 8u * slot;
+#if defined(VC_DOT_PROBE) && VC_DOT_PROBE == 2
+        amb_arrive(fb);                            // probe: no loads (consumers compute on whatever the ring holds)
+        return;
+#endif
         amb_expect_tx(fb, 16u * (uint32_t)H * 2u * (SEPV ? 2u : 1u));
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (size_t)slot * slot_elems);
         const int64_t row0 = (int64_t)((int)blockIdx.x + vi * (int)gridDim.x) * T;
@@ -122,9 +126,7 @@ __global__ void __launch_bounds__(kDotThreads, 2) attn_dot_ws_kernel(const AttnD
   pdl_wait();                                      // queries (and the ctx destination) belong to the previous kernels
   pdl_launch_dependents();
   const int w = warp;
-  const int cw = H / kDotCW;                       // features = context columns of this warp
-  const int nmt = cw / 16;                         // m-tiles = k-steps of this warp
-  const bool has_lo = a.q != nullptr;              // fp32 queries: hi + lo bf16 fragments
+  constexpr int cw = 16 * MAXMT;                   // features = context columns of this warp
   const int lrowA = (((lane >> 3) & 1) << 3) + (lane & 7), lcolA = (lane >> 4) << 3;   // ldmatrix (scores): frames x features
   const int lrowT = ((lane >> 4) << 3) + (lane & 7), lcolT = ((lane >> 3) & 1) << 3;   // ldmatrix.trans (context)
   int slot = 0, u = 0;
@@ -132,21 +134,15 @@ __global__ void __launch_bounds__(kDotThreads, 2) attn_dot_ws_kernel(const AttnD
   for (int vi = 0; vi < nvid; ++vi) {
     const int b = (int)blockIdx.x + vi * (int)gridDim.x;
     // ---- query fragments of beam g: features k0 + {2tg, 2tg+1} and + 8 of every k-step
-    uint32_t qh[MAXMT][2], ql[MAXMT][2];
+    uint32_t qh[MAXMT][2];
 #pragma unroll
     for (int i = 0; i < MAXMT; ++i) {
-      qh[i][0] = qh[i][1] = ql[i][0] = ql[i][1] = 0u;
-      if (i < nmt && g < K) {
+      qh[i][0] = qh[i][1] = 0u;
+      if (g < K) {
         const int k0 = w * cw + i * 16 + 2 * tg;
         const int64_t r = (int64_t)b * K + g;
-        if (has_lo) {
-          const float2 x = ld_f2(a.q + r * H + k0), y = ld_f2(a.q + r * H + k0 + 8);
-          split_bf16x2(x.x * a.scale, x.y * a.scale, qh[i][0], ql[i][0]);
-          split_bf16x2(y.x * a.scale, y.y * a.scale, qh[i][1], ql[i][1]);
-        } else {
-          qh[i][0] = ld_u32(a.q_act + r * a.q_ld + k0);
-          qh[i][1] = ld_u32(a.q_act + r * a.q_ld + k0 + 8);
-        }
+        qh[i][0] = ld_u32(a.q_act + r * a.q_ld + k0);
+        qh[i][1] = ld_u32(a.q_act + r * a.q_ld + k0 + 8);
       }
     }
     float c[MAXMT][4];
@@ -158,24 +154,25 @@ __global__ void __launch_bounds__(kDotThreads, 2) attn_dot_ws_kernel(const AttnD
 
     for (int ft = 0; ft < NT; ++ft, ++u) {
       amb_wait(full + 8u * slot, par);
+#if defined(VC_DOT_PROBE) && VC_DOT_PROBE == 1
+      __syncwarp();                                // probe: no compute (the producer / HBM side alone)
+      if (lane == 0) amb_arrive(empty + 8u * slot);
+      ring_adv(slot, par, 1, nslots);
+      continue;
+#endif
       const uint32_t ktile = (uint32_t)__cvta_generic_to_shared(ring + (size_t)slot * slot_elems);
       const uint32_t vtile = ktile + (SEPV ? (uint32_t)tile_elems * 2u : 0u);
       // ---- scores of beam g for frames ft*16 + {2tg, 2tg+1, 2tg+8, 2tg+9}, per head of this warp
       float xs[HP][4];
       if constexpr (HPW == 0) {
-        // (hi and lo query parts, even and odd k-steps: four independent accumulation chains)
-        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, s3[4] = {0.f, 0.f, 0.f, 0.f};
+        // (even and odd k-steps: two independent accumulation chains)
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < MAXMT; ++i) {
-          if (i < nmt) {
-            uint32_t a0, a1, a2, a3;
-            ldmatrix_x4(ktile + (uint32_t)(lrowA * pitch + w * cw + i * 16 + lcolA) * 2u, a0, a1, a2, a3);
-            mma_bf16((i & 1) ? s2 : s0, a0, a1, a2, a3, qh[i][0], qh[i][1]);
-            if (has_lo) mma_bf16((i & 1) ? s3 : s1, a0, a1, a2, a3, ql[i][0], ql[i][1]);
-          }
+          uint32_t a0, a1, a2, a3;
+          ldmatrix_x4(ktile + (uint32_t)(lrowA * pitch + w * cw + i * 16 + lcolA) * 2u, a0, a1, a2, a3);
+          mma_bf16((i & 1) ? s1 : s0, a0, a1, a2, a3, qh[i][0], qh[i][1]);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { s0[j] += s2[j]; s1[j] += s3[j]; }
         // accumulator layout: {S[g][2tg], S[g][2tg+1], S[g+8][2tg], S[g+8][2tg+1]} (frame, beam) -> exchange [beam][frame]
         float* pp = part + (size_t)((u & 1) * kDotCW + w) * 128;
         pp[(2 * tg) * 16 + g] = s0[0] + s1[0];
@@ -203,8 +200,7 @@ __global__ void __launch_bounds__(kDotThreads, 2) attn_dot_ws_kernel(const AttnD
             const int i = hh * NKH + j;
             uint32_t a0, a1, a2, a3;
             ldmatrix_x4(ktile + (uint32_t)(lrowA * pitch + w * cw + i * 16 + lcolA) * 2u, a0, a1, a2, a3);
-            mma_bf16(s0, a0, a1, a2, a3, qh[i][0], qh[i][1]);
-            if (has_lo) mma_bf16(s1, a0, a1, a2, a3, ql[i][0], ql[i][1]);
+            mma_bf16((j & 1) ? s1 : s0, a0, a1, a2, a3, qh[i][0], qh[i][1]);
           }
           // the head's score tile is complete in this warp: (frame, beam) accumulator layout -> (beam g, 4 frames) per lane
           const float v0 = s0[0] + s1[0], v1 = s0[1] + s1[1], v2 = s0[2] + s1[2], v3 = s0[3] + s1[3];
@@ -230,7 +226,7 @@ __global__ void __launch_bounds__(kDotThreads, 2) attn_dot_ws_kernel(const AttnD
 #pragma unroll
       for (int hh = 0; hh < HP; ++hh) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) xs[hh][i] = dead[i] ? -INFINITY : (masked[i] ? -1e9f : xs[hh][i]);
+        for (int i = 0; i < 4; ++i) xs[hh][i] = dead[i] ? -INFINITY : (masked[i] ? -1e9f : xs[hh][i] * a.scale);
         // ---- online softmax over the tile (the 4 lanes of a group hold the 16 frames of beam g)
         float tmax = fmaxf(fmaxf(xs[hh][0], xs[hh][1]), fmaxf(xs[hh][2], xs[hh][3]));
         tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
@@ -256,7 +252,7 @@ __global__ void __launch_bounds__(kDotThreads, 2) attn_dot_ws_kernel(const AttnD
 #pragma unroll
         for (int j = 0; j < (HPW > 0 ? NKH : MAXMT); ++j) {
           const int i = (HPW > 0 ? hh * NKH : 0) + j;
-          if (HPW > 0 || i < nmt) {
+          {
             if (ft > 0) { c[i][0] *= sc0; c[i][1] *= sc1; c[i][2] *= sc0; c[i][3] *= sc1; }
             uint32_t a0, a1, a2, a3;
             ldmatrix_x4_trans(vtile + (uint32_t)(lrowT * pitch + w * cw + i * 16 + lcolT) * 2u, a0, a1, a2, a3);
@@ -281,7 +277,7 @@ __global__ void __launch_bounds__(kDotThreads, 2) attn_dot_ws_kernel(const AttnD
     const int k0 = 2 * tg, k1 = 2 * tg + 1;
 #pragma unroll
     for (int i = 0; i < MAXMT; ++i) {
-      if (i < nmt) {
+      {
         const int hh = HPW > 0 ? i / NKH : 0;
         const int col0 = w * cw + i * 16;
         if (k0 < K) { out_s[k0 * H + col0 + g] = __float2bfloat16_rn(c[i][0] * i0[hh]); out_s[k0 * H + col0 + g + 8] = __float2bfloat16_rn(c[i][2] * i0[hh]); }
@@ -299,30 +295,34 @@ inline bool attn_dot_enabled() {       // VC_DISABLE_ATTN_DOT=1: generic kernel 
   const char* e = getenv("VC_DISABLE_ATTN_DOT");
   return !(e != nullptr && e[0] == '1');
 }
-// heads = 1 for the Luong forms.  sepv: separate value tile.
+// heads = 1 for the Luong forms.  sepv: separate value tile (multi-head).
 inline bool attn_dot_ws_ok(int K, int H, int T, int heads, bool sepv, bool weights) {
-  if (!attn_dot_enabled() || weights || K < 1 || K > 8 || T < 1 || H % (16 * kDotCW) != 0 || H > 1024 || heads < 1) return false;
+  if (!attn_dot_enabled() || weights || K < 1 || K > 8 || T < 1 || heads < 1) return false;
+  if (!(H == 128 || H == 256 || H == 512 || H == 1024)) return false;
+  const int cw = attn_dot_warps(H);
+  if (sepv != (heads > 1)) return false;           // (single-head attention over separate K / V tiles: generic kernel)
   if (heads > 1) {
-    const int nmt = H / (16 * kDotCW), hpw = heads / kDotCW;
-    if (heads % kDotCW != 0 || !(hpw == 1 || hpw == 2) || !(nmt == 2 || nmt == 4 || nmt == 8) || nmt % hpw != 0) return false;
+    const int nmt = H / (16 * cw), hpw = heads / cw;
+    if (heads % cw != 0 || !(hpw == 1 || hpw == 2) || nmt % hpw != 0) return false;
   }
   const size_t slot = (size_t)(sepv ? 2 : 1) * 16 * (H + kEncPad) * 2;
-  const size_t fixed = 1024 * kDotCW + (size_t)K * H * 2 + 2 * kDotMaxSlots * 8;
+  const size_t fixed = 1024 * (size_t)cw + (size_t)K * H * 2 + 2 * kDotMaxSlots * 8;
   return fixed + 2 * slot <= 225 * 1024;
 }
 
 inline int launch_attn_dot_ws(AttnDotArgs a, cudaStream_t stream) {
   const bool sepv = a.values != a.skeys;
   VC_CHECK(attn_dot_ws_ok(a.K, a.H, a.T, a.heads, sepv, false), "dot attention (ws): K=%d H=%d T=%d heads=%d not supported", a.K, a.H, a.T, a.heads);
-  VC_CHECK(a.ctx_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ctx) & 15) == 0 && (a.q != nullptr || (a.q_ld % 2 == 0 && (reinterpret_cast<uintptr_t>(a.q_act) & 3) == 0)),
+  VC_CHECK(a.ctx_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ctx) & 15) == 0 && a.q_ld % 2 == 0 && (reinterpret_cast<uintptr_t>(a.q_act) & 3) == 0,
            "dot attention (ws): ctx must be 16-byte aligned, queries 4-byte aligned");
+  const int cw = attn_dot_warps(a.H);
   const size_t slot = (size_t)(sepv ? 2 : 1) * 16 * (a.H + kEncPad) * 2;
-  const size_t fixed = 1024 * kDotCW + (size_t)a.K * a.H * 2 + 2 * kDotMaxSlots * 8;
+  const size_t fixed = 1024 * (size_t)cw + (size_t)a.K * a.H * 2 + 2 * kDotMaxSlots * 8;
   // two CTAs per SM when at least 3 slots fit into half an SM's shared memory (the other CTA's tiles keep HBM busy while
   // this one finishes a video), else one CTA with as many slots as fit
   int per_sm = 2;
-  size_t ns = (113 * 1024 - fixed) / slot;
-  if (fixed > 113 * 1024 || ns < 3) {
+  size_t ns = fixed < 113 * 1024 ? (113 * 1024 - fixed) / slot : 0;
+  if (ns < 3) {
     per_sm = 1;
     ns = (225 * 1024 - fixed) / slot;
   }
@@ -330,29 +330,34 @@ inline int launch_attn_dot_ws(AttnDotArgs a, cudaStream_t stream) {
   const size_t smem = fixed + (size_t)a.nslots * slot;
   const int cap = per_sm * attn_num_sms();
   const int grid = a.B < cap ? a.B : cap;
-  const int nmt = (a.H + 16 * kDotCW - 1) / (16 * kDotCW);
-  const int hpw = a.heads > 1 ? a.heads / kDotCW : 0;
-#define VC_DOT_LAUNCH(MT, HW, SV)                                                                      \
+  const int hpw = a.heads > 1 ? a.heads / cw : 0;
+#define VC_DOT_LAUNCH(CW, MT, HW)                                                                      \
   do {                                                                                                 \
-    auto kern = attn_dot_ws_kernel<MT, HW, SV>;                                                        \
+    auto kern = attn_dot_ws_kernel<CW, MT, HW>;                                                        \
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    VC_CUDA(launch_pdl(kern, dim3(grid), dim3(kDotThreads), smem, stream, a));                         \
+    VC_CUDA(launch_pdl(kern, dim3(grid), dim3(32 * (CW + 1)), smem, stream, a));                       \
   } while (0)
-#define VC_DOT_BY_MT(HW, SV)                                           \
+#define VC_DOT_SINGLE(CW, MT) VC_DOT_LAUNCH(CW, MT, 0)
+#define VC_DOT_MHA(CW, MT)                                             \
   do {                                                                 \
-    if (nmt <= 2) VC_DOT_LAUNCH(2, HW, SV);                            \
-    else if (nmt <= 4) VC_DOT_LAUNCH(4, HW, SV);                       \
-    else VC_DOT_LAUNCH(8, HW, SV);                                     \
+    if (hpw == 1) VC_DOT_LAUNCH(CW, MT, 1);                            \
+    else VC_DOT_LAUNCH(CW, MT, 2);                                     \
   } while (0)
-  if (hpw == 0) {
-    if (sepv) VC_DOT_BY_MT(0, true);
-    else VC_DOT_BY_MT(0, false);
-  } else if (hpw == 1) {
-    VC_DOT_BY_MT(1, true);
+  if (a.H == 1024) {
+    if (hpw == 0) VC_DOT_SINGLE(4, 16);
+    else VC_DOT_MHA(4, 16);
+  } else if (a.H == 512) {
+    if (hpw == 0) VC_DOT_SINGLE(8, 4);
+    else VC_DOT_MHA(8, 4);
+  } else if (a.H == 256) {
+    if (hpw == 0) VC_DOT_SINGLE(8, 2);
+    else VC_DOT_MHA(8, 2);
   } else {
-    VC_DOT_BY_MT(2, true);
+    if (hpw == 0) VC_DOT_SINGLE(8, 1);
+    else VC_DOT_LAUNCH(8, 1, 1);
   }
-#undef VC_DOT_BY_MT
+#undef VC_DOT_MHA
+#undef VC_DOT_SINGLE
 #undef VC_DOT_LAUNCH
   VC_CUDA(cudaGetLastError());
   return VC_OK;

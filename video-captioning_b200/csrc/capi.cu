@@ -707,38 +707,45 @@ int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64
       return launch_attn_step<ActT, ActT, ATTN_DOT, P>(a, s);
     }
     case VC_ATTN_LUONG_GENERAL: {
-      {
-        VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
-        VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, H, H), hq_cols, estore<float, false, P>(w.Q, H, nullptr), s)));  // :128
-      }
       if constexpr (!P) {
         if (attn_dot_ws_ok(K, H, T, 1, false, attn_out != nullptr) && ctx_ld % 8 == 0) {
+          // streaming kernel: the projected query leaves the GEMM as bf16, like every other activation of the bf16 mode
+          bf16* q16 = reinterpret_cast<bf16*>(w.Q);
+          {
+            VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
+            VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, H, H), hq_cols, estore<bf16, false, P>(q16, H, nullptr), s)));  // :128
+          }
           AttnDotArgs da;
           memset(&da, 0, sizeof(da));
-          da.skeys = da.values = w.enc_act; da.q = w.Q; da.mask = mask; da.ctx = ctx; da.ctx_ld = ctx_ld;
+          da.skeys = da.values = w.enc_act; da.q_act = q16; da.q_ld = H; da.mask = mask; da.ctx = ctx; da.ctx_ld = ctx_ld;
           da.B = B; da.K = K; da.T = T; da.H = H; da.heads = 1; da.scale = 1.f;
           VC_SCOPE(VC_CLS_ATTN_STEP);
           return launch_attn_dot_ws(da, s);
         }
+      }
+      {
+        VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
+        VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, H, H), hq_cols, estore<float, false, P>(w.Q, H, nullptr), s)));  // :128
       }
       a.skeys = w.enc_act; a.q = w.Q; a.D = H;
       VC_SCOPE(VC_CLS_ATTN_STEP);
       return launch_attn_step<ActT, ActT, ATTN_DOT, P>(a, s);
     }
     case VC_ATTN_MULTIHEAD: {
-      {
-        VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
-        VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, H, H), hq_cols, estore<float, false, P>(w.Q, H, m->bq), s)));    // :240
-      }
       a.skeys = w.keys; a.values = w.vals; a.q = w.Q; a.D = H; a.heads = d.num_heads;
       a.scale = 1.0f / sqrtf((float)(H / d.num_heads));
       a.ctx = w.ctx_pre; a.ctx_ld = H;
       bool mha_done = false;
       if constexpr (!P) {
         if (attn_dot_ws_ok(K, H, T, d.num_heads, true, attn_out != nullptr)) {
+          bf16* q16 = reinterpret_cast<bf16*>(w.Q);      // (bf16 query: see the Luong general case)
+          {
+            VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
+            VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, H, H), hq_cols, estore<bf16, false, P>(q16, H, m->bq), s)));    // :240
+          }
           AttnDotArgs da;
           memset(&da, 0, sizeof(da));
-          da.skeys = w.keys; da.values = w.vals; da.q = w.Q; da.mask = mask; da.ctx = w.ctx_pre; da.ctx_ld = H;
+          da.skeys = w.keys; da.values = w.vals; da.q_act = q16; da.q_ld = H; da.mask = mask; da.ctx = w.ctx_pre; da.ctx_ld = H;
           da.B = B; da.K = K; da.T = T; da.H = H; da.heads = d.num_heads; da.scale = a.scale;
           VC_SCOPE(VC_CLS_ATTN_STEP);
           VC_TRY(launch_attn_dot_ws(da, s));
@@ -746,6 +753,10 @@ int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64
         }
       }
       if (!mha_done) {
+        {
+          VC_SCOPE(VC_CLS_ATTN_QUERY_PROJ);
+          VC_TRY((gemm<ActT>(gargs(hq, hq_ld, m->Wq, H, R, H, H), hq_cols, estore<float, false, P>(w.Q, H, m->bq), s)));    // :240
+        }
         VC_SCOPE(VC_CLS_ATTN_STEP);
         VC_TRY((launch_attn_step<ActT, ActT, ATTN_MHA, P>(a, s)));
       }

@@ -243,6 +243,7 @@ enum { EPI_STORE = 0, EPI_LSTM = 1 };
 
 struct alignas(64) TcMaps {
   CUtensorMap A[2], W[2];
+  CUtensorMap Wh[2];      // CTA-pair kernels: W with a 128-row box (each CTA of a pair stages half of the 256-row tile), per z
   // EPI_STORE: io[0] = C.  EPI_LSTM: io[0] = addend (input projections), io[1] = c_prev, io[2] = c_new,
   // io[3] = h destination 0, io[4] = h destination 1.
   CUtensorMap io[5];
@@ -253,6 +254,11 @@ struct TcArgs {
   const float* bias[2];
   int io_col0[5][2];      // column offset of the tile origin inside each io map, per z
   int has_h1;
+  // persistent EPI_LSTM kernel, encoder form: nz = 2 directions share one launch (z is the slowest tile index), and the
+  // all-timestep input projections are ADDED ON THE TENSOR CORES: after the nkb operand k-blocks, four more ring passes bring
+  // the [128 x 64] pieces of the addend tile (A part of the slot only) and one N = 64 MMA each multiplies them by a 64 x 64
+  // identity kept in shared memory into the accumulator's column range -- no epilogue change, no extra staging boxes
+  int nz, has_add;
   // tile-level hand-over between stacked LSTM GEMMs (EpiLstm::sync_*): counters per scheduled m-tile row
   unsigned int* sync_signal;
   const unsigned int* sync_wait;
@@ -597,7 +603,7 @@ template <int EPI, bool CVT = false> struct PersistentCfg {
 // MC: launched as clusters of 2 CTAs (cta_group::2, see the helpers above).  The pair works on the m-tiles (2i, 2i+1) of the
 // same n-tile; both producers signal the leader's full barrier, the leader's MMA completions release the ring slot and
 // publish the accumulator in both CTAs, and both epilogues hand the accumulator back on the leader's barrier
-// (maps.W[1]: W with a 128-row box).
+// (maps.Wh[z]: W with a 128-row box).
 // CVT: A is fp32 in global memory and is NOT staged by TMA: 16 converter warps load it with ld.global.nc (three k-blocks in
 // flight in registers), round to bf16 and write the 128B-swizzled A tile of the ring themselves (fence.proxy.async before
 // the arrive: the MMA reads shared memory through the async proxy).  The feature projection then runs at the bf16 MMA rate
@@ -625,15 +631,16 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
   __shared__ __align__(16) float bias_s[2][BN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const CUtensorMap* mapA = &maps.A[0];
-  const CUtensorMap* mapW = &maps.W[0];
   const int nkb = g.K / BKE;
   // scheduling units: CTAs, or CTA pairs working on pairs of m-tiles (MC; tiles_m is even)
   const int crank = MC ? (int)cluster_ctarank() : 0;
   const int unit = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int units = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int kMT = MC ? 2 : 1;                  // m-tiles per scheduled tile
-  const int num_tiles = (tiles_m / kMT) * tiles_n;
+  const int tiles_z = (tiles_m / kMT) * tiles_n;                                     // tiles of one z (direction)
+  const int num_tiles = tiles_z * ((EPI == EPI_LSTM && g.nz > 1) ? g.nz : 1);
+  const bool has_add = EPI == EPI_LSTM && g.has_add != 0;
+  uint8_t* ident_s = nullptr;                                                        // identity block of the addend MMAs
   // tile schedule (m-major tile index, n fastest): round-robin, or contiguous ranges when the epilogue carries
   // per-row state from tile to tile (STATS)
   const int t_first = STATS ? (int)((int64_t)unit * num_tiles / units) : unit;
@@ -652,8 +659,21 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
     mbar_init(smem_u32(&c_full), 1);
     mbar_init(smem_u32(&c_empty), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(mapA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(mapW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.A[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(MC ? &maps.Wh[0] : &maps.W[0]) : "memory");
+  }
+  if (EPI == EPI_LSTM && has_add) {
+    // 64 x 64 identity, K-major, 128B-swizzled like a W box (MC: this CTA's 32 rows n = 32 * crank + r of it)
+    ident_s = io_smem + 3 * kBoxBytes;
+    constexpr int kRows = MC ? 32 : 64;
+    for (int i = threadIdx.x; i < kRows * 8; i += blockDim.x) {
+      const int r = i >> 3, c = i & 7;                      // row, 16-byte chunk (8 k values)
+      const int n = (MC ? crank * 32 : 0) + r;
+      uint32_t w4[4] = {0u, 0u, 0u, 0u};
+      if ((n >> 3) == c) w4[(n & 7) >> 1] = (n & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 at k = n
+      sts128(swz(smem_u32(ident_s), r, c), w4[0], w4[1], w4[2], w4[3]);
+    }
+    fence_proxy_async_smem();                               // generic-proxy writes -> visible to the tensor core's async proxy
   }
   if (warp == 1) {
     if (MC) tmem_alloc_2sm(smem_u32(&tmem_base_slot), 512);
@@ -665,20 +685,23 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   // operand tiles of a k-block -> ring slot.  MC: this CTA's half of the W tile, completion counted on the leader's barrier
-  auto load_w = [&](uint8_t* sb, uint32_t fb, int k, int n0) {
-    if (MC) tma_load_2d_2sm(smem_u32(sb), &maps.W[1], fb, k, n0 + crank * (BN / 2));
-    else tma_load_2d(smem_u32(sb), mapW, fb, k, n0);
+  auto load_w = [&](uint8_t* sb, uint32_t fb, int k, int n0, int z) {
+    if (MC) tma_load_2d_2sm(smem_u32(sb), &maps.Wh[z], fb, k, n0 + crank * (BN / 2));
+    else tma_load_2d(smem_u32(sb), &maps.W[z], fb, k, n0);
   };
-  auto load_a = [&](uint8_t* sa, uint32_t fb, int acol, int m0) {
-    if (MC) tma_load_2d_2sm(smem_u32(sa), mapA, fb, acol, m0);
-    else tma_load_2d(smem_u32(sa), mapA, fb, acol, m0);
+  auto load_a = [&](uint8_t* sa, uint32_t fb, const CUtensorMap* map, int acol, int m0) {
+    if (MC) tma_load_2d_2sm(smem_u32(sa), map, fb, acol, m0);
+    else tma_load_2d(smem_u32(sa), map, fb, acol, m0);
   };
   // the barrier of a slot is armed once per use, by the leader, for both CTAs' bytes
-  auto arm = [&](uint32_t fb) {
+  auto arm_bytes = [&](uint32_t fb, uint32_t bytes) {
     if (CVT) mbar_expect_tx(fb, kBBytes);                  // the A half of the slot is written by the converter warps
-    else if (!MC) mbar_expect_tx(fb, kStageBytes);
-    else if (crank == 0) mbar_expect_tx(fb, 2 * kStageBytes);
+    else if (!MC) mbar_expect_tx(fb, bytes);
+    else if (crank == 0) mbar_expect_tx(fb, 2 * bytes);
   };
+  auto arm = [&](uint32_t fb) { arm_bytes(fb, kStageBytes); };
+  // tile index -> (z, m-tile row, n-tile)
+  auto tile_z = [&](int tile) { return (EPI == EPI_LSTM && g.nz > 1) ? tile / tiles_z : 0; };
   // an epilogue thread is done with accumulator a: tell the MMA issuer (MC: the leader's barrier, from either CTA)
   auto arrive_tmem_empty = [&](uint32_t bar) {
     if (MC && crank != 0) mbar_arrive_remote(bar, 0u);
@@ -692,7 +715,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
     for (int kb = 0; kb < npre; ++kb) {
       const uint32_t fb = smem_u32(&full_bar[kb]);
       arm(fb);
-      load_w(smem + (size_t)kb * kStageBytes + kABytes, fb, kb * BKE, n0);
+      load_w(smem + (size_t)kb * kStageBytes + kABytes, fb, kb * BKE, n0, tile_z(t_first));
     }
   }
   // everything above overlaps the tail of the previous kernel in the stream.  A kernel that is handed its A rows tile by
@@ -706,10 +729,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
-        const int m0 = ((tile / tiles_n) * kMT + crank) * BM, n0 = (tile % tiles_n) * BN;
+        const int z = tile_z(tile), tz = tile - z * tiles_z;
+        const int m0 = ((tz / tiles_n) * kMT + crank) * BM, n0 = (tz % tiles_n) * BN;
         if (EPI == EPI_LSTM && g.sync_wait != nullptr) {
           // the previous layer's GEMM (still running) publishes its h rows per m-tile row: acquire them
-          const unsigned int* flag = g.sync_wait + tile / tiles_n;
+          const unsigned int* flag = g.sync_wait + tz / tiles_n;
           uint32_t spin = 0;
           while (ld_acquire_gpu_u32(flag) < g.sync_target) {
             if (++spin > (1u << 26)) {
@@ -727,11 +751,21 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
             arm(fb);
           }
           const int k = kb * BKE;
-          const int acol = g.a_col0[0] + k + (k >= g.a_split ? g.a_skip : 0);
+          const int acol = g.a_col0[z] + k + (k >= g.a_split ? g.a_skip : 0);
           uint8_t* sa = smem + (size_t)stage * kStageBytes;
-          if (!CVT) load_a(sa, fb, acol, m0);
-          if (!pre) load_w(sa + kABytes, fb, k, n0);
+          if (!CVT) load_a(sa, fb, &maps.A[z], acol, m0);
+          if (!pre) load_w(sa + kABytes, fb, k, n0, z);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (EPI == EPI_LSTM && has_add) {
+          // the addend tile [128 rows x 256 gate columns] as four A-only ring passes (see TcArgs::has_add)
+          for (int j = 0; j < BN / BK; ++j) {
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            arm_bytes(fb, kABytes);
+            load_a(smem + (size_t)stage * kStageBytes, fb, &maps.io[0], g.io_col0[0][z] + n0 + j * BK, m0);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
         }
         if (EPI == EPI_LSTM) {
           // previous cell state of this tile, needed only by epilogue(it): issued AFTER the operand loads so
@@ -739,8 +773,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           mbar_wait(smem_u32(&c_empty), (uint32_t)((it & 1) ^ 1));
           const uint32_t cb = smem_u32(&c_full);
           mbar_expect_tx(cb, 2 * kBoxBytes);
-          tma_load_2d(smem_u32(io_smem), &maps.io[1], cb, g.io_col0[1][0] + n0 / 4, m0);
-          tma_load_2d(smem_u32(io_smem + kBoxBytes), &maps.io[1], cb, g.io_col0[1][0] + n0 / 4 + 32, m0);
+          tma_load_2d(smem_u32(io_smem), &maps.io[1], cb, g.io_col0[1][z] + n0 / 4, m0);
+          tma_load_2d(smem_u32(io_smem + kBoxBytes), &maps.io[1], cb, g.io_col0[1][z] + n0 / 4 + 32, m0);
         }
       }
     }
@@ -772,6 +806,24 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           if (MC) umma_commit_2sm(smem_u32(&empty_bar[stage]));     // slot free in both CTAs
           else umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (EPI == EPI_LSTM && has_add) {
+          // accumulator[:, 64 j .. 64 j + 63] += addend piece j . I  (N = 64 MMAs against the identity block)
+          constexpr uint32_t idesc64 = make_idesc(64, MC ? 256 : BM);
+          const uint64_t di = make_smem_desc(smem_u32(ident_s));
+          for (int j = 0; j < BN / BK; ++j) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            const uint64_t da = make_smem_desc(smem_u32(smem + (size_t)stage * kStageBytes));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (MC) umma_bf16_2sm(d + (uint32_t)(j * BK), da + (uint64_t)(2 * k), di + (uint64_t)(2 * k), idesc64, 1u);
+              else umma_bf16(d + (uint32_t)(j * BK), da + (uint64_t)(2 * k), di + (uint64_t)(2 * k), idesc64, 1u);
+            }
+            if (MC) umma_commit_2sm(smem_u32(&empty_bar[stage]));
+            else umma_commit(smem_u32(&empty_bar[stage]));
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
         }
         if (MC) umma_commit_2sm(smem_u32(&tmem_full[a]));           // accumulator halves complete in both CTAs
         else umma_commit(smem_u32(&tmem_full[a]));
@@ -1044,12 +1096,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
     } else {
       const int et = threadIdx.x - 64;
       for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
-        const int m0 = ((tile / tiles_n) * kMT + crank) * BM, n0 = (tile % tiles_n) * BN;
+        const int z = tile_z(tile), tz = tile - z * tiles_z;
+        const int m0 = ((tz / tiles_n) * kMT + crank) * BM, n0 = (tz % tiles_n) * BN;
         const int a = it & 1;
         float* bs = bias_s[a];
         for (int i = et; i < BN; i += 128) {
           const int col = n0 + i;
-          bs[i] = (g.bias[0] != nullptr && col < g.N) ? g.bias[0][col] : 0.f;
+          bs[i] = (g.bias[z] != nullptr && col < g.N) ? g.bias[z][col] : 0.f;
         }
         mbar_wait(smem_u32(&c_full), (uint32_t)(it & 1));
         mbar_wait(smem_u32(&tmem_full[a]), (uint32_t)((it >> 1) & 1));
@@ -1091,10 +1144,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         epi_bar_sync();
         if (et == 0) {
           const int u_tile = n0 / 4;
-          tma_store_2d(&maps.io[3], h_box, g.io_col0[3][0] + u_tile, m0);
-          if (g.has_h1) tma_store_2d(&maps.io[4], h_box, g.io_col0[4][0] + u_tile, m0);
-          tma_store_2d(&maps.io[2], c_s, g.io_col0[2][0] + u_tile, m0);
-          tma_store_2d(&maps.io[2], c_s + kBoxBytes, g.io_col0[2][0] + u_tile + 32, m0);
+          tma_store_2d(&maps.io[3], h_box, g.io_col0[3][z] + u_tile, m0);
+          if (g.has_h1) tma_store_2d(&maps.io[4], h_box, g.io_col0[4][z] + u_tile, m0);
+          tma_store_2d(&maps.io[2], c_s, g.io_col0[2][z] + u_tile, m0);
+          tma_store_2d(&maps.io[2], c_s + kBoxBytes, g.io_col0[2][z] + u_tile + 32, m0);
           tma_store_commit();
           tma_store_wait_read();
           mbar_arrive_cta(smem_u32(&c_empty));          // c / h boxes may be refilled for the next tile
@@ -1103,7 +1156,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async;" ::: "memory");
             __threadfence();
-            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(g.sync_signal + tile / tiles_n), "r"(1u) : "memory");
+            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(g.sync_signal + tz / tiles_n), "r"(1u) : "memory");
           }
         }
         epi_bar_sync();                                 // nobody rewrites h_box before the stores have read it
@@ -1349,9 +1402,11 @@ inline bool ctx_handover_ok(int M, int N) {
   const int64_t tiles256 = (int64_t)((M + 127) / 128) * ((N + 255) / 256);
   return !(N >= 256 && tiles256 >= num_sms());
 }
-// maps.W[1] <- the W operand with a 128-row box (each CTA of a pair stages half of the 256-row tile)
+// maps.Wh[z] <- the W operand with a 128-row box (each CTA of a pair stages half of the 256-row tile)
 inline int fill_w_half(TcMaps& mp, const GemmArgs& g, int esize) {
-  return get_map(&mp.W[1], g.W[0], (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, 128u, esize);
+  for (int z = 0; z < 2; ++z)
+    VC_TRY(get_map(&mp.Wh[z], g.W[z < g.nz ? z : 0], (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldw, 128u, esize));
+  return VC_OK;
 }
 
 inline int fill_ab(TcMaps& mp, TcArgs& ta, const GemmArgs& g, int64_t a_cols, int BN, int esize = 2) {
@@ -1562,18 +1617,25 @@ inline int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiLstm<bf16,
     }
   }
   dim3 grid(g.N / 256, (g.M + BM - 1) / BM, g.nz);
-  if (!has_add && g.nz == 1 && (int)(grid.x * grid.y) >= num_sms()) {
+  // persistent kernel: decoder form (one z, no addend), or the encoder's per-timestep form -- both directions in one launch,
+  // input projections added by identity MMAs (TcArgs::has_add); VC_DISABLE_PERSISTENT_ENC_STEP=1: one tile per CTA (A/B)
+  static const bool enc_step_off = getenv("VC_DISABLE_PERSISTENT_ENC_STEP") != nullptr && getenv("VC_DISABLE_PERSISTENT_ENC_STEP")[0] == '1';
+  const bool enc_form = has_add || g.nz != 1;
+  if ((!enc_form || !enc_step_off) && (int)(grid.x * grid.y * grid.z) >= (enc_form ? num_sms() / 2 : num_sms())) {
     constexpr int kStages = 3;
-    const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 3 * kBoxBytes + 1024;
+    const size_t ident = has_add ? 64 * 128 : 0;
+    const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 3 * kBoxBytes + ident + 1024;
     VocabStats vs;
     memset(&vs, 0, sizeof(vs));
     ta.sync_signal = e.sync_signal;
     ta.sync_wait = e.sync_wait;
     ta.sync_target = e.sync_target;
-    if (use_mc((int)grid.y, (int)grid.x)) {
+    ta.nz = g.nz;
+    ta.has_add = has_add ? 1 : 0;
+    if (use_mc((int)grid.y, (int)(grid.x * grid.z))) {
       VC_TRY(fill_w_half(mp, g, 2));
       constexpr int kMcStages = 5;
-      const size_t smem_mc = (size_t)kMcStages * (BM * BK * 2 + 128 * BK * 2) + 3 * kBoxBytes + 1024;
+      const size_t smem_mc = (size_t)kMcStages * (BM * BK * 2 + 128 * BK * 2) + 3 * kBoxBytes + ident + 1024;
       auto kern = gemm_tc_persistent_kernel<kMcStages, EPI_LSTM, bf16, false, false, false, true>;
       VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mc));
       VC_CUDA(launch_pdl_cluster(kern, dim3(num_sms()), dim3(PersistentCfg<EPI_LSTM>::kThreads), smem_mc, stream, 2, mp, ta, (int)grid.y, (int)grid.x, vs));
