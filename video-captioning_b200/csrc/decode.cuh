@@ -355,10 +355,15 @@ struct SelScratch {
 
 // One warp selects for one video.  cand_val / cand_idx: the video's [K][K] per-row candidates (row k's j-th best
 // log-prob and token), in global or shared memory.
+// pre_score / pre_alive / pre_hist (all or none): the video's K beam scores, alive flags and token-history rows (step <= 32
+// entries each), staged in shared memory by the caller before its dependency wait -- they are older than the caller's
+// predecessor kernel, so their global round trips need not sit behind the selection's own.
 template <int NQ>   // candidate slots per lane: K*K <= 32*NQ
 __device__ __forceinline__ void beam_select_video(const BeamState& bs, const float* cand_val, const int* cand_idx,
                                                   SelScratch& sm, int b, int K, int V, int S, int step, int end_id,
-                                                  float length_penalty, int* __restrict__ parent, int* __restrict__ cur_tok) {
+                                                  float length_penalty, int* __restrict__ parent, int* __restrict__ cur_tok,
+                                                  const float* pre_score = nullptr, const unsigned char* pre_alive = nullptr,
+                                                  const int (*pre_hist)[32] = nullptr) {
   const int lane = threadIdx.x & 31;
   const int* hin = bs.hist[step & 1];
   int* hout = bs.hist[(step + 1) & 1];
@@ -374,8 +379,8 @@ __device__ __forceinline__ void beam_select_video(const BeamState& bs, const flo
     cf[q] = 0x7fffffff;
     if (c < KK) {
       const int k = c / K;
-      if (bs.alive[r0 + k]) {
-        cv[q] = bs.scores[r0 + k] + cand_val[c];                                          // :211
+      if (pre_alive != nullptr ? pre_alive[k] : bs.alive[r0 + k]) {
+        cv[q] = (pre_score != nullptr ? pre_score[k] : bs.scores[r0 + k]) + cand_val[c];  // :211
         cf[q] = k * V + cand_idx[c];                                                      // flat index of :215
       }
     }
@@ -457,7 +462,7 @@ __device__ __forceinline__ void beam_select_video(const BeamState& bs, const flo
       hv[k] = 0;
       if (k < K && i < step) {
         const int src = (k < n_alive) ? r0 + sm.np[k] : r0 + k;
-        hv[k] = hin[(int64_t)src * S + i];
+        hv[k] = pre_hist != nullptr ? pre_hist[src - r0][i] : hin[(int64_t)src * S + i];
       }
     }
 #pragma unroll
@@ -533,8 +538,10 @@ __device__ __forceinline__ void reorder_row_warp(const DecState<ActT>& st, int64
 // HBM traffic per row: (nc + 2 np) * 4 + K * 128 bytes instead of 4 * V.
 // KMAX: compile-time bound of the beam size (loops are unrolled to it); MAXCL: chunk maxima per lane held in
 // registers (nc <= 32 * MAXCL).
+// All videos of a 1024-video step are resident at once when 7 CTAs fit an SM (K <= 5: 160 threads, <= 56 registers); with 6
+// the step ran as two waves of the kernel's own latency (ncu: launch__waves_per_multiprocessor 1.15, 25 us).
 template <int KMAX, int MAXCL>
-__global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, const float* logits, int64_t ld,
+__global__ void __launch_bounds__(KMAX * 32, (KMAX <= 5 && MAXCL <= 10) ? 7 : 1) select_fused_kernel(BeamState bs, const float* logits, int64_t ld,
                                                                  const float* cmax, const float2* part,
                                                                  int nc, int np, int B, int K, int V, int S, int step, int end_id,
                                                                  float length_penalty, int* __restrict__ parent,
@@ -543,10 +550,23 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
   __shared__ float s_cv[KMAX * KMAX];
   __shared__ int s_ci[KMAX * KMAX];
   __shared__ SelScratch scratch;
+  __shared__ float s_score[KMAX];
+  __shared__ unsigned char s_alive[KMAX];
+  __shared__ int s_hist[KMAX][32];
   const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;     // warp k <-> beam row k of video b
   const int b = blockIdx.x;
   const int64_t r = (int64_t)b * K + k;
   constexpr float kL2e = 1.4426950408889634f;
+  // beam state written by the PREVIOUS step's selection (older than the vocabulary GEMM in front of this kernel): loaded
+  // before the dependency wait, staged in shared memory for warp 0's per-video selection
+  const bool pre = !greedy && step <= 32;
+  int hpre = 0;
+  float spre = 0.f;
+  unsigned char apre = 0;
+  if (pre) {
+    if (lane < step) hpre = bs.hist[step & 1][r * S + lane];
+    if (lane == 0) { spre = bs.scores[r]; apre = bs.alive[r]; }
+  }
   pdl_wait();                 // logits / cmax / part come from the vocabulary GEMM just before (read with ld.cg: PDL, common.cuh)
   pdl_launch_dependents();
   if (lane == 0 && rowthr != nullptr) rowthr[r] = (int)0x80808080;     // the GEMM's shared pruning threshold of this row, for the next step
@@ -557,6 +577,10 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
   for (int i = 0; i < MAXCL; ++i) {
     const int c = lane + 32 * i;
     cv[i] = (c < nc) ? __ldcg(cmax + r * nc + c) : -INFINITY;
+  }
+  if (pre) {
+    s_hist[k][lane] = hpre;
+    if (lane == 0) { s_score[k] = spre; s_alive[k] = apre; }
   }
   // 1. log-sum-exp of the row
   float lse;
@@ -639,7 +663,9 @@ __global__ void __launch_bounds__(KMAX * 32) select_fused_kernel(BeamState bs, c
     return;
   }
   __syncthreads();
-  if (k == 0) beam_select_video<(KMAX * KMAX + 31) / 32>(bs, s_cv, s_ci, scratch, b, K, V, S, step, end_id, length_penalty, parent, cur_tok);
+  if (k == 0)
+    beam_select_video<(KMAX * KMAX + 31) / 32>(bs, s_cv, s_ci, scratch, b, K, V, S, step, end_id, length_penalty, parent, cur_tok,
+                                               pre ? s_score : nullptr, pre ? s_alive : nullptr, pre ? s_hist : nullptr);
   if (!do_reorder) return;
   // reorder fused into the selection: warp k moves row k of this video (parent / token were written by warp 0 above)
   __syncthreads();
