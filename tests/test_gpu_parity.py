@@ -536,18 +536,22 @@ def test_fused_select_equals_streaming_select(monkeypatch, shape, V, B, K):
     T, F = cfg.model.video_sequence_length, cfg.model.cnn_feature_dim
     x = torch.from_numpy(synth.make_features(B, T, F, seed=4)).cuda()
     outs = []
-    for disable in ("1", "0"):
+    # streaming selection; fused selection (candidates above the GEMM's shared row threshold); fused selection without the
+    # shared threshold (every chunk is a candidate: the re-scanning rounds of select_fused_kernel)
+    for disable, no_thr in (("1", "0"), ("0", "0"), ("0", "1")):
         monkeypatch.setenv("VC_DISABLE_FUSED_SELECT", disable)      # read when the native handle is created
+        monkeypatch.setenv("VC_DISABLE_SHARED_THR", no_thr)
         m = make_native_model(cfg, V, sd, "bahdanau", "bf16")
         bm = m.generate(x, START, END, max_length=12, method="beam", beam_size=K)
         gr = m.generate(x, START, END, max_length=12, method="greedy")
         torch.cuda.synchronize()
         outs.append((bm["generated_tokens"].cpu(), bm["lengths"].cpu(), bm["scores"].cpu() if "scores" in bm else None,
                      gr["generated_tokens"].cpu()))
-    (t0, l0, s0, g0), (t1, l1, s1, g1) = outs
-    assert torch.equal(t0, t1) and torch.equal(l0, l1) and torch.equal(g0, g1)
-    if s0 is not None:
-        assert torch.allclose(s0, s1, rtol=1e-5, atol=1e-5)     # log-sum-exp merged in a different order
+    (t0, l0, s0, g0) = outs[0]
+    for (t1, l1, s1, g1) in outs[1:]:
+        assert torch.equal(t0, t1) and torch.equal(l0, l1) and torch.equal(g0, g1)
+        if s0 is not None:
+            assert torch.allclose(s0, s1, rtol=1e-5, atol=1e-5)     # log-sum-exp merged in a different order
 
 
 # ------------------------------------------------------------------ real ("diverse") beam search + n-best
@@ -802,6 +806,34 @@ def test_config3_shape_large_batch_vs_oracle(att):
     ended = t[rows][torch.arange(len(rows)), ll - 1] == END
     exp = torch.where(ended, lpo / (ll - 1).double(), lpo)
     assert float(((sc[rows] - exp).abs() / exp.abs()).max()) < BF16_LOGIT_TOL, (sc[rows], exp)
+
+
+@pytest.mark.parametrize("shape,B", [("c3", 300), ("c3", 512), ("msvd", 1200)])
+def test_encoder_step_gemm_forms_agree(monkeypatch, shape, B):
+    """The encoder's per-timestep LSTM GEMM in its persistent form (both directions per launch, input projections added by
+    identity MMAs on the tensor cores; single CTAs at an odd m-tile count, CTA pairs otherwise) against the one-tile-per-CTA
+    kernel with the staged addend, and -- at H = 512 -- against the weights-stationary persistent recurrence."""
+    from oracle import synth
+    cfg = synth.make_config(shape)
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, "luong_dot", seed=17)
+    T, F = cfg.model.video_sequence_length, cfg.model.cnn_feature_dim
+    x = torch.randn(B, T, F, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    inp = torch.full((B, 2), START, dtype=torch.long, device="cuda")
+    outs = []
+    for off in ("0", "1"):
+        monkeypatch.setenv("VC_DISABLE_PERSISTENT_ENC_STEP", off)
+        monkeypatch.setenv("VC_DISABLE_PERSISTENT_LSTM", "1")        # read when the native handle is created
+        m = make_native_model(cfg, V, sd, "luong_dot", "bf16")
+        outs.append(m(x, inp, None)["encoder_outputs"].float().cpu())
+        del m
+    monkeypatch.delenv("VC_DISABLE_PERSISTENT_ENC_STEP")
+    assert rel_err(outs[0], outs[1]) < 1e-2
+    if shape == "msvd":
+        monkeypatch.setenv("VC_DISABLE_PERSISTENT_LSTM", "0")
+        m = make_native_model(cfg, V, sd, "luong_dot", "bf16")
+        ref = m(x, inp, None)["encoder_outputs"].float().cpu()
+        assert rel_err(outs[0], ref) < 1e-2
 
 
 # ------------------------------------------------------------------ round-1 advisor findings

@@ -541,7 +541,7 @@ __device__ __forceinline__ void reorder_row_warp(const DecState<ActT>& st, int64
 // All videos of a 1024-video step are resident at once when 7 CTAs fit an SM (K <= 5: 160 threads, <= 56 registers); with 6
 // the step ran as two waves of the kernel's own latency (ncu: launch__waves_per_multiprocessor 1.15, 25 us).
 template <int KMAX, int MAXCL>
-__global__ void __launch_bounds__(KMAX * 32, (KMAX <= 5 && MAXCL <= 10) ? 7 : 1) select_fused_kernel(BeamState bs, const float* logits, int64_t ld,
+__global__ void __launch_bounds__(KMAX * 32, KMAX <= 5 ? 7 : 1) select_fused_kernel(BeamState bs, const float* logits, int64_t ld,
                                                                  const float* cmax, const float2* part,
                                                                  int nc, int np, int B, int K, int V, int S, int step, int end_id,
                                                                  float length_penalty, int* __restrict__ parent,
@@ -553,6 +553,8 @@ __global__ void __launch_bounds__(KMAX * 32, (KMAX <= 5 && MAXCL <= 10) ? 7 : 1)
   __shared__ float s_score[KMAX];
   __shared__ unsigned char s_alive[KMAX];
   __shared__ int s_hist[KMAX][32];
+  __shared__ float s_cand_v[KMAX][64];
+  __shared__ int s_cand_i[KMAX][64];
   const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;     // warp k <-> beam row k of video b
   const int b = blockIdx.x;
   const int64_t r = (int64_t)b * K + k;
@@ -569,14 +571,53 @@ __global__ void __launch_bounds__(KMAX * 32, (KMAX <= 5 && MAXCL <= 10) ? 7 : 1)
   }
   pdl_wait();                 // logits / cmax / part come from the vocabulary GEMM just before (read with ld.cg: PDL, common.cuh)
   pdl_launch_dependents();
-  if (lane == 0 && rowthr != nullptr) rowthr[r] = (int)0x80808080;     // the GEMM's shared pruning threshold of this row, for the next step
+  // The GEMM's shared pruning threshold of this row (largest "K-th best chunk maximum" any of its epilogue threads saw: a lower
+  // bound of the true K-th best chunk maximum), read before it is reset for the next step.  Chunks below it cannot be among the K
+  // best, so instead of K arg-max rounds over all nc maxima (10 or 32 registers per lane live across the rounds: 113 registers and
+  // 2.3 waves at V = 30k) the maxima are streamed once, the 30-40 candidates at or above the threshold are compacted into shared
+  // memory (two per lane) and the K rounds run on those.  More than 64 candidates (threshold off, many ties): the rounds re-scan
+  // the maxima from L2, each picking the next chunk after the previous winner in (value desc, index asc) order.
+  // Up to 320 chunks (V <= 10k) the register form is the faster one (20 vs 27 us per step at V = 10k; 58 -> 49 us at V = 30k).
+  constexpr bool kRegs = MAXCL <= 10;
+  const float thr_row = (rowthr != nullptr) ? key2f(__ldcg(rowthr + r)) : -INFINITY;
+  __syncwarp();
+  if (lane == 0 && rowthr != nullptr) rowthr[r] = (int)0x80808080;
 
   // chunk maxima first (the longest dependent chain starts here)
-  float cv[MAXCL];
+  float* cand_v = s_cand_v[k];
+  int* cand_i = s_cand_i[k];
+  int n_cand = 0;
+  float cvr[kRegs ? MAXCL : 1];
+  if constexpr (kRegs) {
 #pragma unroll
-  for (int i = 0; i < MAXCL; ++i) {
-    const int c = lane + 32 * i;
-    cv[i] = (c < nc) ? __ldcg(cmax + r * nc + c) : -INFINITY;
+    for (int i = 0; i < MAXCL; ++i) {
+      const int c = lane + 32 * i;
+      cvr[i] = (c < nc) ? __ldcg(cmax + r * nc + c) : -INFINITY;
+    }
+  } else {
+    constexpr int G = 8;                                  // maxima per lane in flight at a time
+    static_assert(MAXCL % G == 0, "chunk groups");
+#pragma unroll 1
+    for (int i0 = 0; i0 < MAXCL; i0 += G) {
+      if (32 * i0 >= nc) break;
+      float cv[G];
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int c = lane + 32 * (i0 + i);
+        cv[i] = (c < nc) ? __ldcg(cmax + r * nc + c) : -INFINITY;
+      }
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const bool is = cv[i] >= thr_row && cv[i] > -INFINITY;
+        const unsigned bm = __ballot_sync(0xffffffffu, is);
+        if (is) {
+          const int pos = n_cand + __popc(bm & ((1u << lane) - 1u));
+          if (pos < 64) { cand_v[pos] = cv[i]; cand_i[pos] = lane + 32 * (i0 + i); }
+        }
+        n_cand += __popc(bm);
+      }
+    }
+    __syncwarp();
   }
   if (pre) {
     s_hist[k][lane] = hpre;
@@ -608,6 +649,15 @@ __global__ void __launch_bounds__(KMAX * 32, (KMAX <= 5 && MAXCL <= 10) ? 7 : 1)
   // 2. K best chunks; 3a. this lane's element of each
   float val[KMAX];
   int cidx[KMAX];
+  const bool fast = n_cand <= 64;             // (warp-uniform)
+  float v0 = -INFINITY, v1 = -INFINITY;
+  int i0 = 0x7fffffff, i1 = 0x7fffffff;
+  if (!kRegs && fast) {
+    if (lane < n_cand) { v0 = cand_v[lane]; i0 = cand_i[lane]; }
+    if (lane + 32 < n_cand) { v1 = cand_v[lane + 32]; i1 = cand_i[lane + 32]; }
+  }
+  float pv = INFINITY;                        // previous winner (slow path)
+  int pi = -1;
 #pragma unroll
   for (int sel = 0; sel < KMAX; ++sel) {
     val[sel] = -INFINITY;
@@ -615,15 +665,35 @@ __global__ void __launch_bounds__(KMAX * 32, (KMAX <= 5 && MAXCL <= 10) ? 7 : 1)
     if (sel < K) {
       float bv = -INFINITY;
       int bi = 0x7fffffff;
+      if constexpr (kRegs) {
 #pragma unroll
-      for (int i = 0; i < MAXCL; ++i)
-        if (cv[i] > bv) { bv = cv[i]; bi = lane + 32 * i; }     // ascending i: the first maximum has the lowest chunk index
+        for (int i = 0; i < MAXCL; ++i)
+          if (cvr[i] > bv) { bv = cvr[i]; bi = lane + 32 * i; }     // ascending i: the first maximum has the lowest chunk index
+      } else if (fast) {
+        // candidates were compacted in ascending chunk order per maxima pass, not globally: compare indices explicitly
+        if (i0 != 0x7fffffff) { bv = v0; bi = i0; }
+        if (i1 != 0x7fffffff && (v1 > bv || (v1 == bv && i1 < bi))) { bv = v1; bi = i1; }
+      } else {
+        for (int c = lane; c < nc; c += 32) {
+          const float v = __ldcg(cmax + r * nc + c);
+          const bool after = v < pv || (v == pv && c > pi);          // not selected yet
+          if (after && v > -INFINITY && (v > bv || (v == bv && c < bi))) { bv = v; bi = c; }
+        }
+      }
       float wv;
       int wi;
       warp_argmax(bi != 0x7fffffff, bv, bi, wv, wi);
+      if constexpr (kRegs) {
 #pragma unroll
-      for (int i = 0; i < MAXCL; ++i)
-        if (lane + 32 * i == wi) cv[i] = -INFINITY;
+        for (int i = 0; i < MAXCL; ++i)
+          if (lane + 32 * i == wi) cvr[i] = -INFINITY;
+      } else if (fast) {
+        if (i0 == wi) i0 = 0x7fffffff;
+        if (i1 == wi) i1 = 0x7fffffff;
+      } else {
+        pv = wv;
+        pi = wi;
+      }
       if (wi != 0x7fffffff) {
         const int col = wi * 32 + lane;
         cidx[sel] = col;

@@ -1619,7 +1619,8 @@ inline int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiLstm<bf16,
   dim3 grid(g.N / 256, (g.M + BM - 1) / BM, g.nz);
   // persistent kernel: decoder form (one z, no addend), or the encoder's per-timestep form -- both directions in one launch,
   // input projections added by identity MMAs (TcArgs::has_add); VC_DISABLE_PERSISTENT_ENC_STEP=1: one tile per CTA (A/B)
-  static const bool enc_step_off = getenv("VC_DISABLE_PERSISTENT_ENC_STEP") != nullptr && getenv("VC_DISABLE_PERSISTENT_ENC_STEP")[0] == '1';
+  const char* eso = getenv("VC_DISABLE_PERSISTENT_ENC_STEP");       // read per call: tests toggle it inside one process
+  const bool enc_step_off = eso != nullptr && eso[0] == '1';
   const bool enc_form = has_add || g.nz != 1;
   if ((!enc_form || !enc_step_off) && (int)(grid.x * grid.y * grid.z) >= (enc_form ? num_sms() / 2 : num_sms())) {
     constexpr int kStages = 3;
