@@ -132,6 +132,7 @@ struct vc_model {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool disable_ctx_handover = false;      // VC_DISABLE_CTX_HANDOVER=1: the context projection waits for the last LSTM GEMM as a whole (A/B testing)
   bool disable_layer_sync = false;        // VC_DISABLE_LAYER_SYNC=1: stacked decoder LSTM GEMMs in plain stream order (A/B testing)
+  bool disable_vocab_handover = false;    // VC_DISABLE_VOCAB_HANDOVER=1: the vocabulary projection waits for the context projection as a whole (A/B testing)
   bool disable_shared_thr = false;        // VC_DISABLE_SHARED_THR=1: per-CTA pruning thresholds only in the vocab GEMM (A/B testing)
   bool disable_fused_select = false;      // VC_DISABLE_FUSED_SELECT=1: stream the whole logits row in the selection (A/B testing)
   // derived, operand-typed (float or bf16 according to d.precision)
@@ -415,7 +416,7 @@ WS<ActT> carve(const vc_model_desc_t& d, void* base, int B, int T, int K, int S)
     w.vs_cmax = c.take<float>(R * 8 * tn);
     w.vs_part = c.take<float2>(R * 2 * tn);
     w.vs_rowthr = c.take<int>(R);
-    w.dec_sync = c.take<unsigned int>((size_t)d.dec_layers * ((R + 127) / 128));
+    w.dec_sync = c.take<unsigned int>((size_t)(d.dec_layers + 1) * ((R + 127) / 128));   // + context -> vocabulary projection
   }
   w.cand_val = c.take<float>(R * K);
   w.cand_idx = c.take<int>(R * K);
@@ -818,7 +819,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
   const int sync_rows = (R + 127) / 128;
   if constexpr (!P) {
     if (L > 1 && !m->disable_layer_sync && w.dec_sync != nullptr) sync_arr = tc::lstm_sync_arrivals(R, 4 * H);
-    if (sync_arr) VC_CUDA(cudaMemsetAsync(w.dec_sync, 0, sizeof(unsigned int) * (size_t)L * sync_rows, s));
+    if (sync_arr) VC_CUDA(cudaMemsetAsync(w.dec_sync, 0, sizeof(unsigned int) * (size_t)(L + 1) * sync_rows, s));
   }
   {
     VC_SCOPE(VC_CLS_MISC);
@@ -920,6 +921,14 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       }
     }
     // tanh(context_projection([h_top ; ctx ; emb])) (:157-165), operands read in place from Z
+    const int vtn = (V + 255) / 256;
+    // bf16 mode: the GEMM epilogue also emits per-row chunk maxima + log-sum-exp partials, and the selection
+    // reads those instead of the whole logits row (decode.cuh: select_fused_kernel)
+    const bool fused_sel = !P && mode != DM_TEACHER && !m->disable_fused_select && V >= 256 && 8 * vtn <= 1024 &&
+                           (mode == DM_BEAM || p.temperature == 1.0f);
+    // context projection -> vocabulary projection hand-over: the 128x128-tile context kernel signals per 128-row tile, the
+    // vocabulary GEMM (statistics form, single CTAs) starts on the tile rows that are complete while the rest is still running
+    const bool vocab_handover = !P && sync_arr != 0 && fused_sel && !m->disable_vocab_handover && tc::ctx_handover_ok(R, H) && H % 128 == 0;
     {
       GemmArgs g = gargs(w.Z, ZW, m->Wc, 2 * H + E, R, H, 2 * H + E);
       g.a_split = E + H;
@@ -930,6 +939,8 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
         g.sync_target = sync_arr * (unsigned int)(step + 1);
         g.sync_row_shift = tc::lstm_sync_row_shift(R, 4 * H);
       }
+      // ... and its own rows go to the vocabulary projection the same way (flags per 128-row tile, one arrival per n-tile)
+      if (vocab_handover) g.sync_signal = w.dec_sync + (size_t)L * sync_rows;
       VC_SCOPE(VC_CLS_DEC_CONTEXT_PROJ);
       VC_TRY((gemm<ActT>(g, ZW, estore<ActT, true, P>(w.O, H, m->bc), s)));
     }
@@ -939,11 +950,6 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
     const bool tf_direct = mode == DM_TEACHER && Vu == V;
     float* lg = tf_direct ? teacher_logits + (size_t)step * V : w.logits;
     const int64_t ldl = tf_direct ? (int64_t)S * V : V;
-    const int vtn = (V + 255) / 256;
-    // bf16 mode: the GEMM epilogue also emits per-row chunk maxima + log-sum-exp partials, and the selection
-    // reads those instead of the whole logits row (decode.cuh: select_fused_kernel)
-    const bool fused_sel = !P && mode != DM_TEACHER && !m->disable_fused_select && V >= 256 && 8 * vtn <= 1024 &&
-                           (mode == DM_BEAM || p.temperature == 1.0f);
     {
       VC_SCOPE(VC_CLS_DEC_VOCAB);
       if constexpr (!P) {
@@ -954,7 +960,12 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
           vs.rowthr = m->disable_shared_thr ? nullptr : w.vs_rowthr;
           vs.dbg = m->dbg_vocab;
           vs.topk = K <= 8 ? K : 0;     // chunks that cannot be among the row's K best are never written
-          VC_TRY(gemm_vocab_stats(gargs(w.O, H, m->Wv, H, R, V, H), H, estore<float, false, false>(lg, ldl, m->bv), s, vs));
+          GemmArgs gv = gargs(w.O, H, m->Wv, H, R, V, H);
+          if (vocab_handover) {
+            gv.sync_wait = w.dec_sync + (size_t)L * sync_rows;
+            gv.sync_target = (unsigned int)(H / 128) * (unsigned int)(step + 1);
+          }
+          VC_TRY(gemm_vocab_stats(gv, H, estore<float, false, false>(lg, ldl, m->bv), s, vs));
         } else {
           VC_TRY((gemm<ActT>(gargs(w.O, H, m->Wv, H, R, V, H), H, estore<float, false, P>(lg, ldl, m->bv), s)));
         }
@@ -1126,6 +1137,8 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   m->disable_ctx_handover = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_LAYER_SYNC");
   m->disable_layer_sync = env != nullptr && env[0] == '1';
+  env = getenv("VC_DISABLE_VOCAB_HANDOVER");
+  m->disable_vocab_handover = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_SHARED_THR");
   m->disable_shared_thr = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_FUSED_SELECT");

@@ -29,6 +29,10 @@ struct GemmArgs {
   const unsigned int* sync_wait;
   unsigned int sync_target;
   int sync_row_shift;
+  // ... and the producer side of the same protocol for a plain-store GEMM on the 128x128 tensor-core kernel (the context
+  // projection hands its rows over to the vocabulary projection): sync_signal[m0 >> 7] is incremented once per finished tile,
+  // after its stores have completed.  nullptr: no signalling.
+  unsigned int* sync_signal;
 };
 
 // ---------------------------------------------------------------- plain store (+bias, +tanh)

@@ -450,7 +450,15 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs g) {
           tma_store_commit();
         }
       }
-      if (et == 0) tma_store_wait_read();
+      if (et == 0) {
+        tma_store_wait_read();
+        if (g.sync_signal != nullptr) {
+          // publish this tile's rows to the consumer GEMM (GemmArgs::sync_signal): stores complete, then a release increment
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          asm volatile("fence.proxy.async;" ::: "memory");
+          asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(g.sync_signal + (m0 >> 7)), "r"(1u) : "memory");
+        }
+      }
     } else {
       // ---- fused LSTM cell: 8 hidden units (32 gate columns) per TMEM load
       constexpr int kUnits = BN / 4;                                 // 64
@@ -731,8 +739,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
         const int z = tile_z(tile), tz = tile - z * tiles_z;
         const int m0 = ((tz / tiles_n) * kMT + crank) * BM, n0 = (tz % tiles_n) * BN;
-        if (EPI == EPI_LSTM && g.sync_wait != nullptr) {
-          // the previous layer's GEMM (still running) publishes its h rows per m-tile row: acquire them
+        if (g.sync_wait != nullptr) {
+          // the producer GEMM (still running: the previous LSTM layer, or the context projection in front of the vocabulary
+          // projection) publishes its rows per m-tile row: acquire them
           const unsigned int* flag = g.sync_wait + tz / tiles_n;
           uint32_t spin = 0;
           while (ld_acquire_gpu_u32(flag) < g.sync_target) {
@@ -1416,6 +1425,7 @@ inline int fill_ab(TcMaps& mp, TcArgs& ta, const GemmArgs& g, int64_t a_cols, in
   memset(&ta, 0, sizeof(ta));
   ta.M = g.M; ta.N = g.N; ta.K = g.K; ta.a_split = g.a_split; ta.a_skip = g.a_skip;
   ta.sync_wait = g.sync_wait; ta.sync_target = g.sync_target; ta.sync_row_shift = g.sync_row_shift;
+  ta.sync_signal = g.sync_signal;
   for (int z = 0; z < 2; ++z) {
     const int zz = z < g.nz ? z : 0;
     int c0 = 0;
@@ -1459,7 +1469,10 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
   VC_TRY(fill_ab(mp, ta, g, a_cols, BN));
   ta.bias[0] = ta.bias[1] = e.bias[0];
   VC_TRY(get_map(&mp.io[0], e.C[0], (uint64_t)g.M, (uint64_t)g.N, (uint64_t)e.ldc, BM, sizeof(OutT)));
-  if (BN == 256) ta.sync_wait = nullptr;   // tile-level hand-over (GemmArgs::sync_wait) is a feature of the 128x128-tile kernel
+  // consumer side of the tile-level hand-over (GemmArgs::sync_wait): the 128x128-tile kernel, and the single-CTA persistent
+  // kernel with the vocabulary statistics (flags per 128-row m-tile); producer side (sync_signal): the 128x128-tile kernel
+  if (BN == 256 && stats == nullptr) ta.sync_wait = nullptr;
+  if (BN == 256) ta.sync_signal = nullptr;
   if (BN == 256) {
     // persistent, TMEM double-buffered: one CTA per SM loops over the tiles
     // (4 stages + staging + static smem would exceed the 227 KB limit)
@@ -1470,6 +1483,7 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
     // (measured 72 vs 68 us); VC_MC_STATS=1 pairs it anyway
     static const bool mc_stats = getenv("VC_MC_STATS") != nullptr && getenv("VC_MC_STATS")[0] == '1';
     const bool mc = use_mc(tm, tn) && (stats == nullptr || mc_stats);
+    if (mc) ta.sync_wait = nullptr;          // (pair tiles span two 128-row flag rows)
     if (mc) VC_TRY(fill_w_half(mp, g, 2));
     const int ctas = mc ? num_sms() : (tm * tn < num_sms() ? tm * tn : num_sms());
     VocabStats vs;
