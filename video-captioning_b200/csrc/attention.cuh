@@ -391,7 +391,15 @@ struct AttnAddArgs {
   // the next CTAs.  nullptr: no gate.
   int* sm_sem;
   int sem_limit;
+#ifdef VC_ATTN_PROBE
+  long long* dbg;        // probe builds (scripts/attn_ws_probe.cu): clock64 stamps of CTA 0, [unit][event]
+#endif
 };
+#ifdef VC_ATTN_PROBE
+#define ATTN_PROBE(cond, unit, ev) do { if (a.dbg != nullptr && blockIdx.x == 0 && (cond) && (unit) < 64) a.dbg[(unit) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define ATTN_PROBE(cond, unit, ev) do { } while (0)
+#endif
 
 constexpr int kAddThreads = 128;
 
@@ -953,6 +961,7 @@ __global__ void __launch_bounds__(32 * (4 * NG + 4 * NCG + 1), 1) attn_additive_
     }
     while (u < total) {
       const int b = (int)blockIdx.x + vi * (int)gridDim.x;
+      ATTN_PROBE(sw == 0 && lane == 0, u, 0);
       // next unit of this group
       int vin = vi, ftn = ft + NG;
       while (ftn >= NT) { ftn -= NT; ++vin; }
@@ -1010,7 +1019,9 @@ __global__ void __launch_bounds__(32 * (4 * NG + 4 * NCG + 1), 1) attn_additive_
         key0 = nx0;
         key1 = nx1;
       }
+      ATTN_PROBE(sw == 0 && lane == 0, u, 1);
       amb_wait(part_empty + 8u * pslot, ppar ^ 1u);
+      ATTN_PROBE(sw == 0 && lane == 0, u, 2);
       if (tg == 0) {
         float* pp = part + (size_t)(pslot * 4 + sw) * K * 16;
 #pragma unroll
@@ -1049,7 +1060,9 @@ __global__ void __launch_bounds__(32 * (4 * NG + 4 * NCG + 1), 1) attn_additive_
       float m_run = -1e30f, l_run = 0.f;
       for (int ft = 0; ft < NT; ++ft) {
         // scores of beam g for frames ft*16 + {2tg, 2tg+1, 2tg+8, 2tg+9}
+        ATTN_PROBE(cw == 0 && lane == 0, vi * NT + ft, 4);
         amb_wait(part_full + 8u * pslot, ppar);
+        ATTN_PROBE(cw == 0 && lane == 0, vi * NT + ft, 5);
         float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
         if (g < K) {
           const float* pp = part + (size_t)pslot * 4 * K * 16 + g * 16 + 2 * tg;
@@ -1103,6 +1116,7 @@ __global__ void __launch_bounds__(32 * (4 * NG + 4 * NCG + 1), 1) attn_additive_
         split_bf16x2(pv[2], pv[3], bh1, bl1);
         // context: ctx^T[col, beam] += enc[t, col] * p[beam, t]
         amb_wait(enc_full + 8u * eslot, epar);
+        ATTN_PROBE(cw == 0 && lane == 0, vi * NT + ft, 6);
         const uint32_t tile = (uint32_t)__cvta_generic_to_shared(enc_s + (size_t)eslot * 16 * pitch);
 #pragma unroll
         for (int i = 0; i < MAXMT; ++i) {
@@ -1115,6 +1129,7 @@ __global__ void __launch_bounds__(32 * (4 * NG + 4 * NCG + 1), 1) attn_additive_
           }
         }
         __syncwarp();
+        ATTN_PROBE(cw == 0 && lane == 0, vi * NT + ft, 7);
         if (lane == 0) amb_arrive(enc_empty + 8u * eslot);
         ring_adv(eslot, epar, 1, kWsEncSlots);
       }
