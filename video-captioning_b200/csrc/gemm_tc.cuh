@@ -266,7 +266,16 @@ struct TcArgs {
   int sync_row_shift;     // gemm_tc_kernel: counter index = m0 >> sync_row_shift
   const float* a32;       // CVT kernels: the fp32 A operand [M, lda32] (converted to bf16 by the producer warps)
   int64_t lda32;
+#ifdef VC_GEMM_PROBE
+  long long* dbg;         // probe builds (scripts/gemm_probe.cu): clock64 stamps of CTA 0 of the persistent kernel, [tile][event]
+#endif
 };
+#ifdef VC_GEMM_PROBE
+inline long long*& probe_dbg() { static long long* p = nullptr; return p; }   // set by the probe before a launch
+#define GEMM_PROBE(it, ev) do { if (g.dbg != nullptr && blockIdx.x == 0 && (it) < 16) g.dbg[(it) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define GEMM_PROBE(it, ev) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------- the kernel
 // EPI_STORE: OutT = float | bf16, optional tanh.   EPI_LSTM: BN = 256 (64 hidden units per tile),
@@ -752,6 +761,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           }
           asm volatile("fence.proxy.async;" ::: "memory");   // order the acquire before the async-proxy loads
         }
+        GEMM_PROBE(it, 0);
         for (int kb = 0; kb < nkb; ++kb) {
           const bool pre = (it == 0 && kb < npre);         // W already on its way, barrier already armed
           const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -797,9 +807,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         const int a = it & 1;
         mbar_wait(smem_u32(&tmem_empty[a]), (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained accumulator a
         tc_fence_after();
+        GEMM_PROBE(it, 1);
         const uint32_t d = tmem_base + (uint32_t)(a * BN);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
+          if (kb == 0) GEMM_PROBE(it, 2);
           tc_fence_after();
           uint8_t* sa = smem + (size_t)stage * kStageBytes;
           const uint64_t da = make_smem_desc(smem_u32(sa));
@@ -836,6 +848,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         }
         if (MC) umma_commit_2sm(smem_u32(&tmem_full[a]));           // accumulator halves complete in both CTAs
         else umma_commit(smem_u32(&tmem_full[a]));
+        GEMM_PROBE(it, 3);
       }
     }
   } else if (CVT && warp >= 2 + PersistentCfg<EPI, CVT>::kEpiWarps) {
@@ -1116,6 +1129,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         mbar_wait(smem_u32(&c_full), (uint32_t)(it & 1));
         mbar_wait(smem_u32(&tmem_full[a]), (uint32_t)((it >> 1) & 1));
         tc_fence_after();
+        if (et == 0) GEMM_PROBE(it, 4);
         epi_bar_sync();                                  // bias staged by all
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
         const uint32_t c_s = smem_u32(io_smem);
@@ -1150,6 +1164,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         tc_fence_before();
         arrive_tmem_empty(smem_u32(&tmem_empty[a]));
         fence_proxy_async_smem();
+        if (et == 0) GEMM_PROBE(it, 5);
         epi_bar_sync();
         if (et == 0) {
           const int u_tile = n0 / 4;
@@ -1159,6 +1174,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           tma_store_2d(&maps.io[2], c_s + kBoxBytes, g.io_col0[2][z] + u_tile + 32, m0);
           tma_store_commit();
           tma_store_wait_read();
+          GEMM_PROBE(it, 6);
           mbar_arrive_cta(smem_u32(&c_empty));          // c / h boxes may be refilled for the next tile
           if (g.sync_signal != nullptr) {
             // publish this tile's h rows to the next layer's GEMM: stores complete, then a release increment
@@ -1647,6 +1663,9 @@ inline int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiLstm<bf16,
     ta.sync_target = e.sync_target;
     ta.nz = g.nz;
     ta.has_add = has_add ? 1 : 0;
+#ifdef VC_GEMM_PROBE
+    ta.dbg = probe_dbg();
+#endif
     if (use_mc((int)grid.y, (int)(grid.x * grid.z))) {
       VC_TRY(fill_w_half(mp, g, 2));
       constexpr int kMcStages = 5;
