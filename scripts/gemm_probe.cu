@@ -28,7 +28,86 @@ __global__ void fill_bf16(bf16* p, size_t n, float scale, unsigned seed) {
 }
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
 
+// vocabulary projection with the selection statistics: gemm_probe vocab [M] [V] [K]
+int vocab_main(int M, int V, int K) {
+  bf16 *A, *W;
+  float *logits, *bias, *cmax;
+  float2* part;
+  int* rowthr;
+  long long* dbg;
+  const int tn = (V + 255) / 256;
+  CK(cudaMalloc(&A, (size_t)M * K * 2));
+  CK(cudaMalloc(&W, (size_t)V * K * 2));
+  CK(cudaMalloc(&logits, (size_t)M * V * 4));
+  CK(cudaMalloc(&bias, (size_t)V * 4));
+  CK(cudaMalloc(&cmax, (size_t)M * 8 * tn * 4));
+  CK(cudaMalloc(&part, (size_t)M * 2 * tn * 8));
+  CK(cudaMalloc(&rowthr, (size_t)M * 4));
+  CK(cudaMalloc(&dbg, 16 * 8 * 8));
+  CK(cudaMemset(dbg, 0, 16 * 8 * 8));
+  CK(cudaMemset(bias, 0, (size_t)V * 4));
+  fill_bf16<<<1024, 256>>>(A, (size_t)M * K, 1.f, 1u);
+  fill_bf16<<<1024, 256>>>(W, (size_t)V * K, 0.05f, 2u);
+  CK(cudaDeviceSynchronize());
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A[0] = g.A[1] = A; g.W[0] = g.W[1] = W; g.lda = K; g.ldw = K; g.M = M; g.N = V; g.K = K; g.nz = 1; g.a_split = 1 << 30;
+  EpiStore<float, false, false> e;
+  memset(&e, 0, sizeof(e));
+  e.C[0] = e.C[1] = logits; e.ldc = V; e.bias[0] = e.bias[1] = bias;
+  tc::VocabStats vs;
+  memset(&vs, 0, sizeof(vs));
+  vs.cmax = cmax; vs.part = part; vs.nc = 8 * tn; vs.np = 2 * tn; vs.rowthr = rowthr; vs.topk = 5;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int modes[6] = {0, 1, 2, 4, 3, 7};    // VocabStats::dbg bits: 1 no logits stores, 2 no exp sums, 4 no statistics stores
+  for (int mi = 0; mi < 6; ++mi) {
+    const int dbgmode = modes[mi];
+    vs.dbg = dbgmode;
+    const int reps = 20;
+    float total = 0.f;
+    for (int i = 0; i < reps + 3; ++i) {
+      CK(cudaMemsetAsync(rowthr, 0x80, (size_t)M * 4, 0));
+      if (i >= 3) cudaEventRecord(e0);
+      if (tc::launch_gemm_tc(g, K, e, 0, &vs) != 0) return 2;
+      if (i >= 3) {
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        total += ms;
+      }
+    }
+    printf("vocab GEMM M=%d V=%d K=%d epilogue parts skipped (dbg bits) %d: %.1f us per launch (%.0f TFLOP/s)\n", M, V, K, dbgmode,
+           total / reps * 1e3, 2.0 * M * V * K / (total / reps * 1e-3) / 1e12);
+  }
+  vs.dbg = 0;
+  CK(cudaMemsetAsync(rowthr, 0x80, (size_t)M * 4, 0));
+  tc::probe_dbg() = dbg;
+  if (tc::launch_gemm_tc(g, K, e, 0, &vs) != 0) return 2;
+  CK(cudaDeviceSynchronize());
+  static long long h[16 * 8];
+  CK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+  long long base = 0;
+  for (int i = 0; i < 128; ++i) if (h[i] && (base == 0 || h[i] < base)) base = h[i];
+  printf("tile: loads_start acc_free first_kb mma_done | epi_acc epi_done   (ns since the first stamp of CTA 0)\n");
+  for (int it = 0; it < 12; ++it) {
+    printf("%2d:", it);
+    for (int ev = 0; ev < 6; ++ev) {
+      if (ev == 4) printf(" |");
+      printf(" %7.0f", h[it * 8 + ev] ? (double)(h[it * 8 + ev] - base) * 1e6 / khz : -1.0);
+    }
+    printf("\n");
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && strcmp(argv[1], "vocab") == 0)
+    return vocab_main(argc > 2 ? atoi(argv[2]) : 5120, argc > 3 ? atoi(argv[3]) : 10000, argc > 4 ? atoi(argv[4]) : 512);
   const int M = argc > 1 ? atoi(argv[1]) : 5120, H = argc > 2 ? atoi(argv[2]) : 512, K = argc > 3 ? atoi(argv[3]) : 1536;
   const int N = 4 * H;
   bf16 *A, *W, *h0, *h1;

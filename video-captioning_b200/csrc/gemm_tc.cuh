@@ -944,9 +944,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         const float thr_in = thr;
         mbar_wait(smem_u32(&tmem_full[a]), (uint32_t)((it >> 1) & 1));
         tc_fence_after();
+        if (warp == 2 && lane == 0) GEMM_PROBE(it, 4);
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // bias of this half staged
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + half * 128);
         const bool tail_tile = n0 + BN > g.N;
+        // (the epilogue paces this kernel: ~4 us per tile against 2.3 us of main loop, scripts/gemm_probe.cu vocab; of the 25 us it
+        // adds to the bare GEMM, ~19 are the keep logic + kept-chunk stores, ~5-10 the exponentials, ~2 the statistics stores;
+        // per-chunk (max, sum) pairs merged after the loop instead of the running pair measured the same)
         float run_m = -1e30f, run_s = 0.f;                // online (max, sum 2^((x-max) log2e)) of this half tile
         float cm[4];
         // TMEM loads are software-pipelined: the load of chunk bx+1 is in flight while chunk bx is processed
@@ -1043,6 +1047,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         }
         tc_fence_before();
         arrive_tmem_empty(smem_u32(&tmem_empty[a]));
+        if (warp == 2 && lane == 0) GEMM_PROBE(it, 5);
         if (shared_thr && thr > thr_in && thr > gthr) atomicMax(vstat.rowthr + row, f2key(thr));
         if (row < g.M && !(vstat.dbg & 4)) {
           *reinterpret_cast<float4*>(vstat.cmax + (size_t)row * vstat.nc + tn * 8 + half * 4) =
@@ -1510,6 +1515,9 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
         VC_CHECK(vs.nc == 8 * tn && vs.np == 2 * tn, "vocab statistics buffers do not match the tiling (nc=%d np=%d tn=%d)", vs.nc, vs.np, tn);
         vs.logits = e.C[0];
         vs.ld = e.ldc;
+#ifdef VC_GEMM_PROBE
+        ta.dbg = probe_dbg();
+#endif
         // no staging boxes: one 144-byte slot per epilogue thread for the sparse row-chunk stores
         constexpr int kStatStages = 3;
         const size_t smem_st = (size_t)kStatStages * (BM * BK * 2 + 256 * BK * 2) + 256 * 144 + 1024;
