@@ -91,15 +91,29 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     sources is stored beside the library, so a library left over from older sources is never loaded silently."""
     if not force and library_is_current():
         return LIB_PATH
-    cmd = nvcc_command(LIB_PATH + ".tmp")
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building libvc_b200.so:\n" + proc.stdout + proc.stderr)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    with open(_HASH_PATH, "w") as fh:
-        fh.write(sources_hash())
-    if verbose:
-        print(proc.stdout + proc.stderr)
+    # One builder at a time across processes (the ranks of a torchrun launch all get here when the library is stale): an
+    # exclusive lock on a side file, the state re-checked under it, a per-process temporary name, an atomic rename.
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and library_is_current():
+                return LIB_PATH
+            tmp = f"{LIB_PATH}.tmp{os.getpid()}"
+            proc = subprocess.run(nvcc_command(tmp), capture_output=True, text=True)
+            if proc.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libvc_b200.so:\n" + proc.stdout + proc.stderr)
+            if os.path.exists(_HASH_PATH):
+                os.remove(_HASH_PATH)          # never a new library beside the old hash
+            os.replace(tmp, LIB_PATH)
+            with open(_HASH_PATH, "w") as fh:
+                fh.write(sources_hash())
+            if verbose:
+                print(proc.stdout + proc.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
