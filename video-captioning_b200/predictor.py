@@ -219,16 +219,17 @@ class VideoCaptionPredictor:
         toks = out["generated_tokens"].cpu()
         attn = out["attention_weights"].cpu() if "attention_weights" in out else None
         lens = out["lengths"].cpu() if "lengths" in out else None
+        rows = toks.tolist()                       # one conversion for the whole matrix
+        if lens is not None:
+            rows = [row[:n] for row, n in zip(rows, lens.tolist())]
+        else:
+            # a per-video (B=1) greedy call stops right after this video's first END (decoder.py:275)
+            end = voc.end_idx
+            rows = [row[: row.index(end) + 1] if end in row else row for row in rows]
+        captions = voc.decode_batch(rows, remove_special_tokens=True)
         results = []
-        for i in range(toks.shape[0]):
-            row = toks[i].tolist()
-            if lens is not None:
-                row = row[: int(lens[i])]
-            else:
-                # a per-video (B=1) greedy call stops right after this video's first END (decoder.py:275)
-                if voc.end_idx in row:
-                    row = row[: row.index(voc.end_idx) + 1]
-            res = {"caption": voc.decode_caption(row, remove_special_tokens=True), "tokens": row, "method": method}
+        for i, (row, cap) in enumerate(zip(rows, captions)):
+            res = {"caption": cap, "tokens": row, "method": method}
             if attn is not None:
                 res["attention_weights"] = attn[i, : len(row)]
             results.append(res)
