@@ -526,6 +526,11 @@ def main():
     prof = _native.profile_end()
     peaks = load_peaks()
     work = class_work(wl, cm, B)
+    if prof.get("reorder_embed", {"scopes": 0})["scopes"] == 0 and "attn_step" in work:
+        # the reorder / embedding gather rode along inside the attention kernel (attention.cuh: RowGather): its bytes are
+        # that kernel's algorithmic bytes now
+        work["attn_step"]["bytes"] += work["reorder_embed"]["bytes"]
+        work["attn_step"]["includes"] = "reorder_embed row gather"
     total_ms = sum(v["ms"] for v in prof.values()) / prof_steps
     breakdown = {}
     for cls, v in prof.items():

@@ -65,6 +65,66 @@ int main(int argc, char** argv) {
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   printf("B=%d T=%d D=%d H=%d K=%d: %.1f us per launch (%.2e tanh/s)\n", B, T, D, H, K, ms / reps * 1e3, (double)R * T * D / (ms / reps * 1e-3));
+  {
+    // the same launch carrying the decoder's row gather (attention.cuh: RowGather): (h, c) of two layers by parent row + the
+    // embedding by token, into strided destinations like run_decode's; checked against the sources afterwards
+    const int V = 10000, E = 512;
+    const size_t ZW = E + 3 * H;
+    vc::bf16 *hn[2], *emb, *Z, *XL;
+    float *cn[2], *cd[2];
+    int *parent, *tok;
+    for (int l = 0; l < 2; ++l) {
+      CK(cudaMalloc(&hn[l], R * H * 2)); CK(cudaMalloc(&cn[l], R * H * 4)); CK(cudaMalloc(&cd[l], R * H * 4));
+      fill16<<<256, 256>>>(hn[l], R * H, 1.f, 10u + l);
+      fill16<<<256, 256>>>(cn[l], R * H, 1.f, 20u + l);
+    }
+    CK(cudaMalloc(&emb, (size_t)V * E * 2)); CK(cudaMalloc(&Z, R * ZW * 2)); CK(cudaMalloc(&XL, R * 2 * H * 2));
+    CK(cudaMemset(Z, 0, R * ZW * 2)); CK(cudaMemset(XL, 0, R * 2 * H * 2));
+    fill16<<<256, 256>>>(emb, (size_t)V * E, 1.f, 30u);
+    int* hp = (int*)malloc(R * 4 * 2);
+    for (size_t r = 0; r < R; ++r) { hp[r] = (int)((r / K) * K + (r * 7 + 3) % K); hp[R + r] = (int)((r * 2654435761u) % V); }
+    CK(cudaMalloc(&parent, R * 4)); CK(cudaMalloc(&tok, R * 4));
+    CK(cudaMemcpy(parent, hp, R * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(tok, hp + R, R * 4, cudaMemcpyHostToDevice));
+    vc::RowGather rg;
+    memset(&rg, 0, sizeof(rg));
+    bool ok = true;
+    for (int l = 0; l < 2; ++l) {
+      ok = ok && vc::row_gather_add(rg, hn[l], H * 2, l == 0 ? (void*)(Z + E + H) : (void*)(XL + H), l == 0 ? ZW * 2 : 2 * H * 2, H * 2, false);
+      ok = ok && vc::row_gather_add(rg, cn[l], H * 4, cd[l], H * 4, H * 4, false);
+    }
+    ok = ok && vc::row_gather_add(rg, emb, E * 2, Z, ZW * 2, E * 2, true);
+    if (!ok) { printf("gather: rows do not fit\n"); return 3; }
+    rg.n_rows = (int)R; rg.V = V; rg.parent = parent; rg.tok = tok;
+    if (getenv("GATHER_DBG")) rg.dbg = atoi(getenv("GATHER_DBG"));
+    for (int i = 0; i < 3; ++i)
+      if (vc::launch_attn_additive_ws(a, K, 0, rg) != 0) return 2;
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i)
+      if (vc::launch_attn_additive_ws(a, K, 0, rg) != 0) return 2;
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("  with the row gather (%d pieces of 512 bytes per row): %.1f us per launch\n", rg.n_pieces, ms / reps * 1e3);
+    // check
+    unsigned short* hz = (unsigned short*)malloc(R * ZW * 2);
+    unsigned short* hh = (unsigned short*)malloc(R * H * 2);
+    unsigned short* he = (unsigned short*)malloc((size_t)V * E * 2);
+    float* hc = (float*)malloc(R * H * 4);
+    float* hcd = (float*)malloc(R * H * 4);
+    CK(cudaMemcpy(hz, Z, R * ZW * 2, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hh, hn[0], R * H * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(he, emb, (size_t)V * E * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hc, cn[1], R * H * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hcd, cd[1], R * H * 4, cudaMemcpyDeviceToHost));
+    size_t bad = 0;
+    for (size_t r = 0; r < R; ++r)
+      for (int c = 0; c < H; ++c) {
+        bad += hz[r * ZW + E + H + c] != hh[(size_t)hp[r] * H + c];
+        bad += hz[r * ZW + c] != he[(size_t)hp[R + r] * E + c];
+        bad += hcd[r * H + c] != hc[(size_t)hp[r] * H + c];
+      }
+    printf("  gather check: %zu mismatches\n", bad);
+    if (bad && !rg.dbg) return 4;
+  }
   a.dbg = dbg;
   if (vc::launch_attn_additive_ws(a, K, 0) != 0) return 2;
   CK(cudaDeviceSynchronize());

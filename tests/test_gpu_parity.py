@@ -463,7 +463,7 @@ def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
 
     def run(**env):
         for k in ("VC_DISABLE_LAYER_SYNC", "VC_DISABLE_CTX_HANDOVER", "VC_DISABLE_MC", "VC_DISABLE_PDL", "VC_DISABLE_SHARED_THR",
-                  "VC_CUDA_GRAPHS", "VC_DISABLE_EARLY_Q", "VC_DISABLE_VOCAB_HANDOVER"):
+                  "VC_CUDA_GRAPHS", "VC_DISABLE_EARLY_Q", "VC_DISABLE_VOCAB_HANDOVER", "VC_DISABLE_ATTN_GATHER"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -486,7 +486,8 @@ def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
     assert same >= 0.9, same          # different attention kernels (v4 / v5): near-ties may flip
     for env in (dict(VC_DISABLE_LAYER_SYNC="1"), dict(VC_DISABLE_CTX_HANDOVER="1"), dict(VC_DISABLE_MC="1"),
                 dict(VC_DISABLE_SHARED_THR="1"), dict(VC_CUDA_GRAPHS="0"), dict(VC_DISABLE_PDL="1"), dict(VC_DISABLE_EARLY_Q="1"),
-                dict(VC_DISABLE_VOCAB_HANDOVER="1"), dict(VC_DISABLE_VOCAB_HANDOVER="1", VC_DISABLE_CTX_HANDOVER="1")):
+                dict(VC_DISABLE_VOCAB_HANDOVER="1"), dict(VC_DISABLE_VOCAB_HANDOVER="1", VC_DISABLE_CTX_HANDOVER="1"),
+                dict(VC_DISABLE_ATTN_GATHER="1")):      # reorder / embedding gather as its own launch vs inside the attention kernel
         got = run(**env)
         for k in ref:
             assert torch.equal(got[k], ref[k]), (env, k)

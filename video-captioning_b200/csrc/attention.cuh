@@ -860,6 +860,51 @@ __device__ __forceinline__ void ring_adv(int& slot, uint32_t& par, int n, int N)
   while (slot >= N) { slot -= N; par ^= 1u; }
 }
 
+// Row gather riding along with the persistent attention kernel (capi.cu:run_decode): the beam reorder of the decoder state
+// and the next tokens' embeddings (video_captioning_model.py:247-249,269-272, decoder.py:130) are pure row copies that only
+// depend on the selection before this kernel and only feed the LSTM GEMM after it.  The attention step is XU-bound and
+// leaves two thirds of the HBM bandwidth unused, so two extra warps move the rows while the scoring warps work.  A row is a
+// list of 512-byte pieces (one 16-byte chunk per lane): piece j of row r comes from row parent[r] (or row tok[r] of a table)
+// of src[j] and goes to row r of dst[j].  All addresses and strides are multiples of 16 bytes.
+// (A first version staged the rows through a shared-memory ring with cp.async.bulk in both directions: correct, but the
+// extra 21-43 KB of shared memory moved the L1 carve-out and its bulk loads queued in front of the encoder tile producer's,
+// +12 us per launch for a 20 us gather; scripts/attn_ws_probe.cu.)
+constexpr int kGatherMaxPieces = 16;  // 8 KB per row: (h, c) of two layers at H = 512 + a 512-wide embedding are 14
+constexpr int kGatherWarps = 2;
+struct RowGather {
+  int n_rows;            // 0: nothing to gather
+  int n_pieces;
+  int V;                 // rows of the token-indexed tables (tokens are clamped)
+  int dbg;               // probe only: 1 = no loads, 2 = no stores
+  const int* parent;     // [n_rows] source row, or nullptr: identity
+  const int* tok;        // [n_rows] token of row r
+  const uint8_t* src[kGatherMaxPieces];
+  uint8_t* dst[kGatherMaxPieces];
+  int64_t src_stride[kGatherMaxPieces], dst_stride[kGatherMaxPieces];   // bytes
+  uint8_t by_tok[kGatherMaxPieces];                                     // 1: source row = tok[r], else parent[r]
+};
+// appends the pieces of one segment (`bytes` per row); false when it is not 512-byte granular / aligned or does not fit
+inline bool row_gather_add(RowGather& rg, const void* src, int64_t src_stride, void* dst, int64_t dst_stride, size_t bytes, bool by_tok) {
+  if (bytes == 0 || bytes % 512 != 0 || src_stride % 16 != 0 || dst_stride % 16 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(dst) & 15) != 0 || rg.n_pieces + (int)(bytes / 512) > kGatherMaxPieces)
+    return false;
+  for (size_t off = 0; off < bytes; off += 512) {
+    const int j = rg.n_pieces++;
+    rg.src[j] = static_cast<const uint8_t*>(src) + off; rg.src_stride[j] = src_stride;
+    rg.dst[j] = static_cast<uint8_t*>(dst) + off; rg.dst_stride[j] = dst_stride;
+    rg.by_tok[j] = by_tok ? 1 : 0;
+  }
+  return true;
+}
+__device__ __forceinline__ uint4 ldcg128(const void* p) {     // L2-coherent: the rows were written by earlier kernels of the loop
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void stcg128(void* p, const uint4& v) {
+  asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // T_weights: number of frames when the attention weights are requested (raw scores are kept per video), else 0
 inline size_t attn_ws_smem_bytes(int K, int D, int H, int NG, int NCG, int T_weights) {
   const int Tp = (T_weights + 15) & ~15;
@@ -870,9 +915,9 @@ inline size_t attn_ws_smem_bytes(int K, int D, int H, int NG, int NCG, int T_wei
 
 // K: exact beam count (<= 8).  Requires D % 32 == 0, D <= 512, H % 64 == 0, H <= 512.
 template <int K, int NG, int NCG>
-__global__ void __launch_bounds__(32 * (4 * NG + 4 * NCG + 1), 1) attn_additive_ws_kernel(const AttnAddArgs a) {
+__global__ void __launch_bounds__(32 * (4 * NG + 4 * NCG + 1 + kGatherWarps), 1) attn_additive_ws_kernel(const AttnAddArgs a, const RowGather rg) {
   constexpr int kScoreWarps = 4 * NG, kCtxWarps = 4 * NCG;
-  constexpr int kThreads = 32 * (kScoreWarps + kCtxWarps + 1);
+  constexpr int kThreads = 32 * (kScoreWarps + kCtxWarps + 1 + kGatherWarps);      // + enc tile producer warp + row gather warps
   extern __shared__ __align__(16) uint8_t smem_u8[];
   const int T = a.T, D = a.D, H = a.H, B = a.B;
   const int NT = (T + 15) >> 4;                  // 16-frame tiles
@@ -1165,16 +1210,45 @@ __global__ void __launch_bounds__(32 * (4 * NG + 4 * NCG + 1), 1) attn_additive_
         named_bar_sync(1 + cg, 128);             // before the next video's scores overwrite sc_s
       }
     }
-  } else if (lane == 0) {
-    // ================= enc tile producer: as far ahead as the ring allows
-    int slot = 0;
-    uint32_t par = 0;
-    ring_adv(slot, par, p_u, kWsEncSlots);
-    for (; p_u < total; ++p_u) {
-      amb_wait(enc_empty + 8u * slot, par ^ 1u);
-      issue_enc(p_vi, p_ft, slot);
-      if (++p_ft == NT) { p_ft = 0; ++p_vi; }
-      ring_adv(slot, par, 1, kWsEncSlots);
+  } else if (warp == kScoreWarps + kCtxWarps) {
+    if (lane == 0) {
+      // ================= enc tile producer: as far ahead as the ring allows
+      int slot = 0;
+      uint32_t par = 0;
+      ring_adv(slot, par, p_u, kWsEncSlots);
+      for (; p_u < total; ++p_u) {
+        amb_wait(enc_empty + 8u * slot, par ^ 1u);
+        issue_enc(p_vi, p_ft, slot);
+        if (++p_ft == NT) { p_ft = 0; ++p_vi; }
+        ring_adv(slot, par, 1, kWsEncSlots);
+      }
+    }
+  } else if (rg.n_rows > 0) {
+    // ================= row gather (RowGather above): warp gw takes rows blockIdx.x + (gw + 2 i) gridDim.x; a row moves in two
+    // batches of up to eight 512-byte pieces (all loads of a batch in flight, then its stores)
+    const int gw = warp - (kScoreWarps + kCtxWarps + 1);
+    const int n_my = (rg.n_rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    for (int i = gw; i < n_my; i += kGatherWarps) {
+      const int r = (int)blockIdx.x + i * (int)gridDim.x;
+      const int64_t p = rg.parent != nullptr ? (int64_t)__ldcg(rg.parent + r) : (int64_t)r;     // written by the previous kernel
+      int tok = __ldcg(rg.tok + r);
+      tok = min(max(tok, 0), rg.V - 1);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int pc = half * 8 + j;
+          v[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (pc < rg.n_pieces && !(rg.dbg & 1))
+            v[j] = ldcg128(rg.src[pc] + (rg.by_tok[pc] ? (int64_t)tok : p) * rg.src_stride[pc] + lane * 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int pc = half * 8 + j;
+          if (pc < rg.n_pieces && !(rg.dbg & 2)) stcg128(rg.dst[pc] + (int64_t)r * rg.dst_stride[pc] + lane * 16, v[j]);
+        }
+      }
     }
   }
 }
@@ -1203,15 +1277,15 @@ inline bool attn_additive_ws_ok(int B, int K, int D, int H, int T, bool weights)
          attn_ws_smem_bytes(K, D, H, cfg / 10, cfg % 10, weights ? T : 0) <= 200 * 1024;
 }
 template <int NG, int NCG>
-int launch_attn_additive_ws_cfg(const AttnAddArgs& a, int K, cudaStream_t stream) {
+int launch_attn_additive_ws_cfg(const AttnAddArgs& a, int K, cudaStream_t stream, const RowGather& rg) {
   const size_t smem = attn_ws_smem_bytes(K, a.D, a.H, NG, NCG, a.attn_out != nullptr ? a.T : 0);
   const int grid = a.B < attn_num_sms() ? a.B : attn_num_sms();
-  constexpr int kThreads = 32 * (4 * NG + 4 * NCG + 1);
+  constexpr int kThreads = 32 * (4 * NG + 4 * NCG + 1 + kGatherWarps);
 #define VC_WS_LAUNCH(KK)                                                                               \
   do {                                                                                                 \
     auto kern = attn_additive_ws_kernel<KK, NG, NCG>;                                                  \
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    VC_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, a));                            \
+    VC_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, a, rg));                        \
   } while (0)
   switch (K) {
     case 1: VC_WS_LAUNCH(1); break;
@@ -1226,16 +1300,16 @@ int launch_attn_additive_ws_cfg(const AttnAddArgs& a, int K, cudaStream_t stream
 #undef VC_WS_LAUNCH
   return VC_OK;
 }
-inline int launch_attn_additive_ws(const AttnAddArgs& a, int K, cudaStream_t stream) {
+inline int launch_attn_additive_ws(const AttnAddArgs& a, int K, cudaStream_t stream, const RowGather& rg = RowGather()) {
   VC_CHECK(attn_additive_ws_ok(a.B, K, a.D, a.H, a.T, a.attn_out != nullptr), "additive attention (ws): B=%d K=%d D=%d H=%d T=%d not supported",
            a.B, K, a.D, a.H, a.T);
   VC_CHECK(a.ctx_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ctx) & 15) == 0, "additive attention (ws): ctx must be 16-byte aligned");
   switch (attn_ws_groups()) {
-    case 31: return launch_attn_additive_ws_cfg<3, 1>(a, K, stream);
-    case 42: return launch_attn_additive_ws_cfg<4, 2>(a, K, stream);
-    case 51: return launch_attn_additive_ws_cfg<5, 1>(a, K, stream);
-    case 52: return launch_attn_additive_ws_cfg<5, 2>(a, K, stream);
-    default: return launch_attn_additive_ws_cfg<4, 1>(a, K, stream);
+    case 31: return launch_attn_additive_ws_cfg<3, 1>(a, K, stream, rg);
+    case 42: return launch_attn_additive_ws_cfg<4, 2>(a, K, stream, rg);
+    case 51: return launch_attn_additive_ws_cfg<5, 1>(a, K, stream, rg);
+    case 52: return launch_attn_additive_ws_cfg<5, 2>(a, K, stream, rg);
+    default: return launch_attn_additive_ws_cfg<4, 1>(a, K, stream, rg);
   }
 }
 

@@ -127,6 +127,7 @@ struct vc_model {
   bool disable_fused_reorder = true;      // VC_FUSED_REORDER=1: the fused selection kernel also does the reorder/embedding gather (measured slower than the separate PDL launch: 54 vs 33 + 20 us per step)
   bool feat_cvt = false;                  // VC_FEAT_CVT=1: feature projection with fp32 -> bf16 converting producer warps instead of tf32 operands
   bool early_attn = false;                // VC_EARLY_ATTN=1: the next step's attention also runs on the second stream, before the reorder
+  bool disable_attn_gather = false;       // VC_DISABLE_ATTN_GATHER=1: reorder / embedding gather as a launch of its own instead of a warp of the attention kernel (A/B testing)
   bool disable_early_q = false;           // VC_DISABLE_EARLY_Q=1: query projection in place, after the reorder (A/B testing)
   cudaStream_t aux_stream = nullptr;      // second stream of the decode loop (early query projection)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -649,7 +650,7 @@ int run_precompute(vc_model* m, WS<ActT>& w, int B, int T, cudaStream_t s) {
 template <class ActT>
 int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64_t hq_cols, const float* mask, int B, int T,
                   int K, ActT* ctx, int64_t ctx_ld, float* attn_out, int64_t attn_ld, cudaStream_t s, bool q_ready = false,
-                  const int* q_rows = nullptr) {
+                  const int* q_rows = nullptr, const RowGather* gather = nullptr) {
   constexpr bool P = std::is_same<ActT, float>::value;
   const vc_model_desc_t& d = m->d;
   const int H = d.hidden_dim, A = d.attn_dim, R = B * K;
@@ -678,7 +679,12 @@ int run_attention(vc_model* m, WS<ActT>& w, const ActT* hq, int64_t hq_ld, int64
           aa.sm_sem = m->attn_gate > 0 ? reinterpret_cast<int*>(w.flags) + 512 : nullptr;   // zeroed by run_decode
           aa.sem_limit = m->attn_gate;
           VC_SCOPE(VC_CLS_ATTN_STEP);
-          if (use_ws) return launch_attn_additive_ws(aa, K, s);
+          if (use_ws) {
+            RowGather none;
+            none.n_rows = 0;
+            return launch_attn_additive_ws(aa, K, s, gather != nullptr ? *gather : none);
+          }
+          VC_CHECK(gather == nullptr, "row gather needs the persistent additive attention kernel");
           if (use_mma) return launch_attn_additive_mma(aa, K, s);
           return launch_attn_additive(aa, K, s);
         }
@@ -784,6 +790,13 @@ bool additive_fast_path(const vc_model* m, int B, int T, int K, int64_t ctx_ld, 
   return !m->disable_attn_v3 && (use_ws || use_mma || attn_additive_fast_ok(K, A, H));
 }
 
+// true when run_attention launches the persistent warp-specialised additive kernel (the one that can carry the row gather)
+template <class ActT>
+bool additive_ws_path(const vc_model* m, int B, int T, int K, int64_t ctx_ld, bool weights) {
+  if (!additive_fast_path<ActT>(m, B, T, K, ctx_ld, weights)) return false;
+  return m->attn_variant >= 5 && attn_additive_ws_ok(B, K, m->d.attn_dim, m->d.hidden_dim, T, weights) && ctx_ld % 8 == 0;
+}
+
 // ---------------------------------------------------------------- decode loop
 enum DecodeMode { DM_GREEDY = 0, DM_BEAM = 1, DM_TEACHER = 2 };
 
@@ -856,14 +869,37 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
   const bool early_attn = early_q && m->early_attn && m->disable_fused_reorder;
   if (early_attn) { st.ctx_src = w.ctx_pre; st.ctx_dst = w.Z + E; st.ctx_ld = ZW; }
   bool attn_pending = false;
+  // Reorder / embedding gather inside the attention kernel (attention.cuh: RowGather): with the queries projected early the
+  // attention step of t+1 reads nothing the gather writes, and the XU-bound kernel leaves most of the HBM bandwidth free, so
+  // the rows move while the scores are computed instead of in a launch of their own between the selection and the attention.
+  RowGather rg;
+  memset(&rg, 0, sizeof(rg));
+  bool gather_in_attn = false;
+  if constexpr (!P) {
+    if (early_q && !early_attn && !m->disable_attn_gather && additive_ws_path<ActT>(m, B, T, K, ZW, attn_out != nullptr)) {
+      bool ok = true;
+      for (int l = 0; ok && l < L; ++l) {
+        ok = row_gather_add(rg, st.h_new[l], (int64_t)H * sizeof(ActT), st.x_rec[l], st.x_ld[l] * (int64_t)sizeof(ActT), H * sizeof(ActT), false) &&
+             row_gather_add(rg, st.c_new[l], (int64_t)H * sizeof(float), st.c[l], (int64_t)H * sizeof(float), H * sizeof(float), false);
+      }
+      ok = ok && row_gather_add(rg, st.emb_table, (int64_t)E * sizeof(ActT), st.emb_dst, st.emb_ld * (int64_t)sizeof(ActT), E * sizeof(ActT), true);
+      rg.n_rows = ok ? R : 0; rg.V = V; rg.tok = w.cur_tok;
+      gather_in_attn = ok;
+    }
+  }
+  bool gather_pending = false;      // the previous step's selection still has to be applied to the decoder state
 
   for (int step = 0; step < S; ++step) {
     // attention on the previous step's top-layer h (decoder.py:135-138) -> ctx segment of Z
     float* aw = attn_out ? attn_out + (size_t)step * T : nullptr;
     if (!(early_attn && step > 0)) {
       if (q_pending) VC_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));
-      VC_TRY((run_attention<ActT>(m, w, hq, hq_ld, hq_cols, mask, B, T, K, w.Z + E, ZW, aw, (int64_t)S * T, s, q_pending, q_rows)));
+      if (gather_pending) VC_CHECK(q_pending, "row gather without early queries");   // (both are set at the end of every step)
+      rg.parent = q_rows;
+      VC_TRY((run_attention<ActT>(m, w, hq, hq_ld, hq_cols, mask, B, T, K, w.Z + E, ZW, aw, (int64_t)S * T, s, q_pending, q_rows,
+                                  gather_pending ? &rg : nullptr)));
       q_pending = false;
+      gather_pending = false;
     }
     // L-layer LSTM, one step (:152): gates = [x | h_prev] . [W_ih | W_hh]^T + (b_ih + b_hh), fused cell
     for (int l = 0; l < L; ++l) {
@@ -1011,7 +1047,9 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       VC_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));
       attn_pending = false;
     }
-    if (step + 1 < S && !reorder_done) {
+    if (step + 1 < S && !reorder_done && gather_in_attn) {
+      gather_pending = true;       // applied by the next step's attention kernel
+    } else if (step + 1 < S && !reorder_done) {
       VC_SCOPE(VC_CLS_REORDER_EMBED);
       VC_CUDA(launch_pdl(reorder_embed_kernel<ActT>, dim3(R), dim3(128), 0, s, st, parent, (const int*)w.cur_tok, V));
     }
@@ -1133,6 +1171,8 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   m->early_attn = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_EARLY_Q");
   m->disable_early_q = env != nullptr && env[0] == '1';
+  env = getenv("VC_DISABLE_ATTN_GATHER");
+  m->disable_attn_gather = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_CTX_HANDOVER");
   m->disable_ctx_handover = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_LAYER_SYNC");
