@@ -57,23 +57,29 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  for (int i = 0; i < 3; ++i)
-    if (vc::tc::launch_lstm_layer_persistent(out, xp, W0, W1, B, T, H, flags, 0) != 0) return 2;
-  CK(cudaDeviceSynchronize());
   const int reps = 10;
-  cudaEventRecord(e0);
-  for (int i = 0; i < reps; ++i)
-    if (vc::tc::launch_lstm_layer_persistent(out, xp, W0, W1, B, T, H, flags, 0) != 0) return 2;
-  cudaEventRecord(e1);
-  CK(cudaDeviceSynchronize());
   float ms = 0.f;
-  cudaEventElapsedTime(&ms, e0, e1);
-  CK(cudaMemset(cs, 0, 8));
-  checksum_kernel<<<512, 256>>>(out, (size_t)B * T * 2 * H, cs);
-  unsigned long long hcs = 0;
-  CK(cudaMemcpy(&hcs, cs, 8, cudaMemcpyDeviceToHost));
-  printf("B=%d T=%d H=%d: %.3f ms per layer (%.2f us per step), checksum %llx\n", B, T, H, ms / reps, ms / reps * 1000.f / T, hcs);
-  if (vc::tc::launch_lstm_layer_persistent(out, xp, W0, W1, B, T, H, flags, 0, dbg) != 0) return 2;
+  const int pair_last = getenv("PROBE_PAIR") ? atoi(getenv("PROBE_PAIR")) : 1;
+  for (int mode = 0; mode < 2; ++mode) {
+    const int pair = mode == 0 ? 1 - pair_last : pair_last;      // both forms on the same operands: the checksums must agree
+    CK(cudaMemset(out, 0, (size_t)B * T * 2 * H * 2));
+    for (int i = 0; i < 3; ++i)
+      if (vc::tc::launch_lstm_layer_persistent(out, xp, W0, W1, B, T, H, flags, 0, nullptr, pair) != 0) return 2;
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i)
+      if (vc::tc::launch_lstm_layer_persistent(out, xp, W0, W1, B, T, H, flags, 0, nullptr, pair) != 0) return 2;
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    cudaEventElapsedTime(&ms, e0, e1);
+    CK(cudaMemset(cs, 0, 8));
+    checksum_kernel<<<512, 256>>>(out, (size_t)B * T * 2 * H, cs);
+    unsigned long long hcs = 0;
+    CK(cudaMemcpy(&hcs, cs, 8, cudaMemcpyDeviceToHost));
+    printf("%s B=%d T=%d H=%d: %.3f ms per layer (%.2f us per step), checksum %llx\n", pair ? "pair  " : "single", B, T, H, ms / reps,
+           ms / reps * 1000.f / T, hcs);
+  }
+  if (vc::tc::launch_lstm_layer_persistent(out, xp, W0, W1, B, T, H, flags, 0, dbg, pair_last) != 0) return 2;
   CK(cudaDeviceSynchronize());
   long long h[8 * 32];
   CK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));

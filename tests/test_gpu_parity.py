@@ -463,7 +463,8 @@ def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
 
     def run(**env):
         for k in ("VC_DISABLE_LAYER_SYNC", "VC_DISABLE_CTX_HANDOVER", "VC_DISABLE_MC", "VC_DISABLE_PDL", "VC_DISABLE_SHARED_THR",
-                  "VC_CUDA_GRAPHS", "VC_DISABLE_EARLY_Q", "VC_DISABLE_VOCAB_HANDOVER", "VC_DISABLE_ATTN_GATHER"):
+                  "VC_CUDA_GRAPHS", "VC_DISABLE_EARLY_Q", "VC_DISABLE_VOCAB_HANDOVER", "VC_DISABLE_ATTN_GATHER", "VC_CTX_PERSISTENT",
+                  "VC_PLSTM_PAIR"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -487,7 +488,9 @@ def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
     for env in (dict(VC_DISABLE_LAYER_SYNC="1"), dict(VC_DISABLE_CTX_HANDOVER="1"), dict(VC_DISABLE_MC="1"),
                 dict(VC_DISABLE_SHARED_THR="1"), dict(VC_CUDA_GRAPHS="0"), dict(VC_DISABLE_PDL="1"), dict(VC_DISABLE_EARLY_Q="1"),
                 dict(VC_DISABLE_VOCAB_HANDOVER="1"), dict(VC_DISABLE_VOCAB_HANDOVER="1", VC_DISABLE_CTX_HANDOVER="1"),
-                dict(VC_DISABLE_ATTN_GATHER="1")):      # reorder / embedding gather as its own launch vs inside the attention kernel
+                dict(VC_DISABLE_ATTN_GATHER="1"),       # reorder / embedding gather as its own launch vs inside the attention kernel
+                dict(VC_CTX_PERSISTENT="1"), dict(VC_CTX_PERSISTENT="2"),      # context projection on the persistent kernels
+                dict(VC_PLSTM_PAIR="1")):               # encoder recurrence on CTA pairs
         got = run(**env)
         for k in ref:
             assert torch.equal(got[k], ref[k]), (env, k)
@@ -670,6 +673,50 @@ def test_reference_beam_scores_vs_oracle(name):
     ended = t[torch.arange(t.shape[0]), l - 1] == END
     exp = torch.where(ended, lpo / (l - 1).double(), lpo)
     assert float(((out["scores"].cpu().double() - exp).abs() / exp.abs()).max()) < BF16_LOGIT_TOL
+
+
+# ------------------------------------------------------------------ reorder / embedding gather inside the attention kernel
+@pytest.mark.parametrize("B,K", [(9, 5), (150, 3)])
+def test_attention_row_gather_diverse_beam(monkeypatch, B, K):
+    """The beam reorder + next-token embedding gather rides inside the persistent additive attention kernel (attention.cuh:
+    RowGather).  With the real (diverse) beam search the parents are a genuine permutation, so a wrong source row, a
+    wrong destination stride or a missed piece shows: n-best tokens, lengths and scores must be bit-identical to the run
+    with the gather as a launch of its own (pure data movement), the best hypothesis' score must be the oracle's
+    log-probability of its tokens (2e-2), and greedy decode (no parents: identity rows) must agree as well.  B = 9 puts one
+    video on each of nine CTAs (gather rows strided over the CTAs), B = 150 more videos than SMs."""
+    from oracle import synth
+    from video_captioning_b200 import _native
+    cfg = synth.make_config("msvd")
+    V = cfg.model.vocab_size
+    sd = synth.make_state_dict(cfg, V, "bahdanau", seed=21, logit_gain=6.0, end_token_id=END, end_bias=0.3)
+    feats = synth.make_features(B, 80, 4096, seed=B)
+    x = torch.from_numpy(feats).cuda()
+    monkeypatch.setenv("VC_ATTN_WS_MIN_B", "1")
+    monkeypatch.setenv("VC_CUDA_GRAPHS", "0")
+    outs = {}
+    for gather_off in ("0", "1"):
+        monkeypatch.setenv("VC_DISABLE_ATTN_GATHER", gather_off)
+        m = make_native_model(cfg, V, sd, "bahdanau", "bf16")
+        n0 = _native.launch_count()
+        o = m.generate(x, START, END, max_length=10, method="beam", beam_size=K, length_penalty=0.7, diverse_beams=True,
+                       num_return_sequences=K)
+        n1 = _native.launch_count()
+        g = m.generate(x, START, END, max_length=10, method="greedy")["generated_tokens"]
+        outs[gather_off] = ({k: v.cpu() for k, v in o.items()}, g.cpu(), n1 - n0)
+    a, b = outs["0"], outs["1"]
+    assert a[2] == b[2] - 9, (a[2], b[2])          # nine reorder launches (steps 1..9) fewer
+    for k in a[0]:
+        assert torch.equal(a[0][k], b[0][k]), k
+    assert torch.equal(a[1], b[1])
+    nt, nl = a[0]["nbest_tokens"], a[0]["nbest_lengths"]
+    # the hypotheses of a video differ (so its beams had different parents / tokens along the way)
+    assert sum(len({tuple(nt[v, j, : nl[v, j]].tolist()) for j in range(K) if nl[v, j] > 0}) > 1 for v in range(B)) >= B - 1
+    rows = [v for v in range(min(B, 12)) if nl[v, 0] > 0]
+    t, l = nt[rows, 0], nl[rows, 0]
+    lpo = make_oracle(sd).sequence_logprob(feats[rows], t, l)
+    exp = lpo / (l - 1).double().pow(0.7)          # completed and live-at-the-end hypotheses alike (vc_beam_nbest)
+    got = a[0]["nbest_scores"][rows, 0].double()
+    assert float(((got - exp).abs() / exp.abs()).max()) < BF16_LOGIT_TOL, (got, exp)
 
 
 # ------------------------------------------------------------------ the benchmarked configuration against the oracle

@@ -127,6 +127,7 @@ struct vc_model {
   bool disable_fused_reorder = true;      // VC_FUSED_REORDER=1: the fused selection kernel also does the reorder/embedding gather (measured slower than the separate PDL launch: 54 vs 33 + 20 us per step)
   bool feat_cvt = false;                  // VC_FEAT_CVT=1: feature projection with fp32 -> bf16 converting producer warps instead of tf32 operands
   bool early_attn = false;                // VC_EARLY_ATTN=1: the next step's attention also runs on the second stream, before the reorder
+  int ctx_persistent = 0;                 // VC_CTX_PERSISTENT=1|2: context projection on the persistent 128x256-tile kernel / its CTA-pair form (A/B testing)
   bool disable_attn_gather = false;       // VC_DISABLE_ATTN_GATHER=1: reorder / embedding gather as a launch of its own instead of a warp of the attention kernel (A/B testing)
   bool disable_early_q = false;           // VC_DISABLE_EARLY_Q=1: query projection in place, after the reorder (A/B testing)
   cudaStream_t aux_stream = nullptr;      // second stream of the decode loop (early query projection)
@@ -964,12 +965,14 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
                            (mode == DM_BEAM || p.temperature == 1.0f);
     // context projection -> vocabulary projection hand-over: the 128x128-tile context kernel signals per 128-row tile, the
     // vocabulary GEMM (statistics form, single CTAs) starts on the tile rows that are complete while the rest is still running
-    const bool vocab_handover = !P && sync_arr != 0 && fused_sel && !m->disable_vocab_handover && tc::ctx_handover_ok(R, H) && H % 128 == 0;
+    const bool ctx_pers = !P && m->ctx_persistent != 0 && H >= 256;
+    const bool vocab_handover = !P && sync_arr != 0 && fused_sel && !m->disable_vocab_handover && tc::ctx_handover_ok(R, H) && H % 128 == 0 && !ctx_pers;
     {
       GemmArgs g = gargs(w.Z, ZW, m->Wc, 2 * H + E, R, H, 2 * H + E);
       g.a_split = E + H;
       g.a_skip = H;
-      if (sync_arr && !m->disable_ctx_handover && tc::ctx_handover_ok(R, H)) {
+      g.force_persistent = ctx_pers ? m->ctx_persistent : 0;
+      if (sync_arr && !m->disable_ctx_handover && tc::ctx_handover_ok(R, H) && !ctx_pers) {
         // rows of h_top are taken over from the last LSTM layer's GEMM tile row by tile row (128x128-tile kernel only)
         g.sync_wait = w.dec_sync + (size_t)(L - 1) * sync_rows;
         g.sync_target = sync_arr * (unsigned int)(step + 1);
@@ -1171,6 +1174,8 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   m->early_attn = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_EARLY_Q");
   m->disable_early_q = env != nullptr && env[0] == '1';
+  env = getenv("VC_CTX_PERSISTENT");
+  m->ctx_persistent = env != nullptr ? atoi(env) : 0;
   env = getenv("VC_DISABLE_ATTN_GATHER");
   m->disable_attn_gather = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_CTX_HANDOVER");

@@ -33,6 +33,9 @@ struct GemmArgs {
   // projection hands its rows over to the vocabulary projection): sync_signal[m0 >> 7] is incremented once per finished tile,
   // after its stores have completed.  nullptr: no signalling.
   unsigned int* sync_signal;
+  // bf16 store GEMMs: 1 = take the persistent 128x256-tile kernel even with fewer tiles than SMs, 2 = its CTA-pair form
+  // (A/B testing of the context projection, VC_CTX_PERSISTENT); both ignore sync_wait / sync_signal
+  int force_persistent;
 };
 
 // ---------------------------------------------------------------- plain store (+bias, +tanh)

@@ -1486,7 +1486,7 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
   TcMaps mp;
   TcArgs ta;
   const int64_t tiles256 = (int64_t)((g.M + 127) / 128) * ((g.N + 255) / 256);
-  const int BN = (stats != nullptr || (g.N >= 256 && tiles256 >= 148)) ? 256 : 128;
+  const int BN = (stats != nullptr || (g.N >= 256 && (tiles256 >= 148 || g.force_persistent != 0))) ? 256 : 128;
   VC_TRY(fill_ab(mp, ta, g, a_cols, BN));
   ta.bias[0] = ta.bias[1] = e.bias[0];
   VC_TRY(get_map(&mp.io[0], e.C[0], (uint64_t)g.M, (uint64_t)g.N, (uint64_t)e.ldc, BM, sizeof(OutT)));
@@ -1503,7 +1503,7 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
     // the vocabulary GEMM (stats) is paced by its epilogue, not by the operand ring: pairing only couples two epilogues
     // (measured 72 vs 68 us); VC_MC_STATS=1 pairs it anyway
     static const bool mc_stats = getenv("VC_MC_STATS") != nullptr && getenv("VC_MC_STATS")[0] == '1';
-    const bool mc = use_mc(tm, tn) && (stats == nullptr || mc_stats);
+    const bool mc = (use_mc(tm, tn) || (g.force_persistent == 2 && tm % 2 == 0 && num_sms() % 2 == 0)) && (stats == nullptr || mc_stats);
     if (mc) ta.sync_wait = nullptr;          // (pair tiles span two 128-row flag rows)
     if (mc) VC_TRY(fill_w_half(mp, g, 2));
     const int ctas = mc ? num_sms() : (tm * tn < num_sms() ? tm * tn : num_sms());

@@ -45,6 +45,10 @@ constexpr int kPlEpiThreads = 256;  // epilogue threads per row-half
 // only lengthen the latency of the first one (0.9 -> 1.5 us) and of everything else that goes through L2.
 constexpr int kPlStages = 3;
 constexpr int kPlBN = 128;          // gate columns per CTA = 32 hidden units
+#ifndef PL_PAIR_STAGES
+#define PL_PAIR_STAGES 3
+#endif
+constexpr int kPlPairStages = PL_PAIR_STAGES;
 
 struct alignas(64) PLstmMaps {
   CUtensorMap out_ld;   // layer output [B, T*2H] bf16, box 64 x 128, 128B swizzle (h_{t-1} loads)
@@ -288,6 +292,216 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
   }
 }
 
+// ---------------------------------------------------------------- CTA-pair form (clusters of 2, tcgen05 cta_group::2)
+// The kernel above is bound by what an SM can take in per step: each CTA needs h_{t-1} of its whole 256-row tile, 256 KB per
+// step through one SM's L2 port (3.3 us of the 7.2 us step; multicasting the boxes inside a cluster does not change what each
+// SM has to receive).  Here two CTAs with neighbouring gate-column tiles form a pair and split the ROWS instead: CTA r of the
+// pair stages only rows [128 r, 128 r + 128) of h_{t-1} (128 KB per step) next to its resident W_hh tile, the leader issues
+// M = 256, N = 256 MMAs (A rows from both CTAs, W columns from both CTAs), and each CTA's TMEM receives its own 128 rows x
+// all 256 gate columns of the pair -- so CTA r runs the cell epilogue of row-half r for 64 hidden units and publishes them.
+// Same grid, same flags (one counter per (direction, row tile, row-half); the NT/2 CTAs that own that half arrive), same
+// arithmetic per element (bit-identical layer outputs, scripts/plstm_probe.cu).  The two row-halves advance in lockstep (one MMA
+// chain per step), which gives up the overlap of one half's epilogue with the other half's main loop that the kernel above has.
+// MEASURED, NOT ADOPTED (opt-in, VC_PLSTM_PAIR=1): 8.7 us per step against 7.2.  The load phase did not shrink with the bytes
+// (128 KB still take 2.2 us after the first box, with 3, 4 or 5 ring stages alike: the 16 MB per step that the 128 CTAs pull
+// out of the same few L2 lines are bound on the L2 side, not at the SM port), and the cell epilogue of all 512 threads at once
+// is MUFU-bound (5 transcendentals x 8192 cell updates per CTA = 1.3 us) on the critical path: flag -> first box 0.9, loads +
+// MMAs 2.2, cell 1.7, stores 0.9, release -> flag 1.5 us.
+// No tmem_empty barrier: the MMAs of step t+1 need both producers' boxes, each producer has acquired its half's flag, and a
+// half's flag includes the CTA's own arrival, which follows its epilogue's TMEM reads.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPlThreads, 1)
+    lstm_layer_pair_kernel(const __grid_constant__ PLstmMaps maps, const PLstmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int H = g.H, T = g.T;
+  const int nkb = H / BK;
+  uint8_t* w_s = smem;                                    // nkb boxes of [128 n x 64 k] bf16: this CTA's half of the pair's W tile
+  uint8_t* a_s = w_s + (size_t)nkb * kBoxBytes;           // kPlPairStages boxes of [128 rows x 64 k]: this CTA's rows of h_{t-1}
+  uint8_t* h_s = a_s + (size_t)kPlPairStages * kBoxBytes;     // 2 x [128 rows x 32 units] bf16 (64B rows): this CTA's rows of h_t
+  __shared__ __align__(8) uint64_t w_bar, full_bar[kPlPairStages], empty_bar[kPlPairStages], tmem_full;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float bias_s[2 * kPlBN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();               // = blockIdx.x & 1: row-half of this CTA
+  const int z = blockIdx.z;                               // direction
+  const int n0 = blockIdx.x * kPlBN;                      // this CTA's W tile (gate columns)
+  const int np0 = (blockIdx.x & ~1) * kPlBN;              // the pair's 256 gate columns = 64 hidden units
+  const int m0 = blockIdx.y * 256 + crank * 128;          // this CTA's rows
+  const int NT = gridDim.x;
+  unsigned int* flag = g.flags + ((size_t)(z * gridDim.y + blockIdx.y) * 2) + crank;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&w_bar), 1);
+    for (int s = 0; s < kPlPairStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 2 * kPlBN) {
+    const float* bz = g.bias[z];
+    bias_s[threadIdx.x] = bz ? bz[np0 + threadIdx.x] : 0.f;
+  }
+  if (warp == 1) tmem_alloc_2sm(smem_u32(&tmem_base_slot), 256);
+  tc_fence_before();
+  cluster_sync_all();                                     // the peer's barriers are initialised before anything is signalled on them
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== W_hh tile (once) + this CTA's rows of h_{t-1} (every step); completion bytes are counted on the leader's barriers =====
+      if (crank == 0) mbar_expect_tx(smem_u32(&w_bar), 2u * (uint32_t)nkb * kBoxBytes);
+      for (int kb = 0; kb < nkb; ++kb)
+        tma_load_2d_2sm(smem_u32(w_s + (size_t)kb * kBoxBytes), &maps.W[z], smem_u32(&w_bar), kb * BK, n0);
+      uint32_t stage = 0, phase = 0;
+      for (int t = 1; t < T; ++t) {
+        const int tprev = (z == 0) ? (t - 1) : (T - t);   // time index holding h_{t-1} of this direction
+        const int col0 = tprev * 2 * H + z * H;
+        // the NT/2 CTAs that own this row-half (one per pair) must have published h_{t-1}
+        const unsigned int need = (unsigned int)(NT / 2) * (unsigned int)t;
+        uint32_t spin = 0;
+        while (ld_acquire_gpu(flag) < need) {
+          if (++spin > (1u << 24)) {
+            printf("vc::lstm_pair flag timeout (block %d,%d,%d step %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, t);
+            __trap();
+          }
+        }
+        PL_PROBE(0 + crank, t);
+        asm volatile("fence.proxy.async;" ::: "memory");   // order the acquire before the async-proxy loads
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          if (crank == 0) mbar_expect_tx(fb, 2u * kBoxBytes);
+          tma_load_2d_2sm(smem_u32(a_s + (size_t)stage * kBoxBytes), &maps.out_ld, fb, col0 + kb * BK, m0);
+          if (++stage == kPlPairStages) { stage = 0; phase ^= 1; }
+        }
+        PL_PROBE(2 + crank, t);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0) {
+      // ===== MMA issuer: the pair's leader, M = 256 (both CTAs' rows) x N = 256 (both CTAs' W tiles) =====
+      constexpr uint32_t idesc = make_idesc(2 * kPlBN, 256);
+      mbar_wait(smem_u32(&w_bar), 0);
+      uint32_t stage = 0, phase = 0;
+      for (int t = 1; t < T; ++t) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          if (kb == 0) PL_PROBE(4, t);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(a_s + (size_t)stage * kBoxBytes));
+          const uint64_t db = make_smem_desc(smem_u32(w_s + (size_t)kb * kBoxBytes));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_2sm(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(smem_u32(&empty_bar[stage]));   // slot free in both CTAs
+          if (++stage == kPlPairStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(smem_u32(&tmem_full));            // both CTAs' accumulator rows are complete
+        PL_PROBE(6, t);
+      }
+    }
+  } else if (warp >= 2 && warp < 18) {
+    // ===== epilogue: fused LSTM cell for this CTA's 128 rows x 64 hidden units, one row x 16 hidden units per thread =====
+    const int sub = (warp - 2) >> 2;                      // which 64 of the pair's 256 gate columns
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                          // row inside the half
+    const int et = (warp - 2) * 32 + lane;                // 0..511
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t hbox = smem_u32(h_s);
+    const int grow = m0 + r;
+    const bool row_ok = grow < g.B;
+    const bf16* xrow = g.xp + (size_t)(row_ok ? grow : 0) * ((size_t)T * 8 * H) + (size_t)z * 4 * H + np0 + sub * 64;
+    float c[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) c[u] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int tt = (z == 0) ? t : (T - 1 - t);
+      uint32_t xw[32];
+      {
+        const bf16* xp_t = xrow + (size_t)tt * 8 * H;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (row_ok) {
+            asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(xw[8 * i + 0]), "=r"(xw[8 * i + 1]), "=r"(xw[8 * i + 2]), "=r"(xw[8 * i + 3]), "=r"(xw[8 * i + 4]),
+                           "=r"(xw[8 * i + 5]), "=r"(xw[8 * i + 6]), "=r"(xw[8 * i + 7])
+                         : "l"(xp_t + 16 * i));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xw[8 * i + j] = 0u;
+          }
+        }
+      }
+      if (t > 0) {
+        mbar_wait(smem_u32(&tmem_full), (uint32_t)((t - 1) & 1));
+        tc_fence_after();
+        if (et == 0) PL_PROBE(8 + crank, t);
+      }
+#pragma unroll
+      for (int cj = 0; cj < 2; ++cj) {
+        const int ci = 2 * sub + cj;                      // 32-column chunk (8 hidden units) of the pair's 256 columns
+        uint32_t v[32];
+        if (t > 0) {
+          tmem_ld32(taddr + (uint32_t)(ci * 32), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;        // h_{-1} = 0: gates = xproj + bias
+        }
+        float gte[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t w = xw[cj * 16 + i];
+          gte[2 * i] = __uint_as_float(v[2 * i]) + bias_s[ci * 32 + 2 * i] + bf16_lo(w);
+          gte[2 * i + 1] = __uint_as_float(v[2 * i + 1]) + bias_s[ci * 32 + 2 * i + 1] + bf16_hi(w);
+        }
+        float hn[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float ig = sigmoid_<false>(gte[4 * u + 0]);
+          const float fg = sigmoid_<false>(gte[4 * u + 1]);
+          const float gg = tanh_<false>(gte[4 * u + 2]);
+          const float og = sigmoid_<false>(gte[4 * u + 3]);
+          const float cn = fmaf(fg, c[cj * 8 + u], ig * gg);
+          c[cj * 8 + u] = cn;
+          hn[u] = og * tanh_<false>(cn);
+        }
+        sts128(swz64(hbox + (uint32_t)(ci >> 2) * (128u * 64u), r, ci & 3), pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]),
+               pack_bf16(hn[4], hn[5]), pack_bf16(hn[6], hn[7]));
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      if (et == 0) PL_PROBE(10 + crank, t);
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      if (et == 0) {
+        const int ucol = tt * 2 * H + z * H + np0 / 4;
+        tma_store_2d(&maps.out_st, hbox, ucol, m0);
+        tma_store_2d(&maps.out_st, hbox + 128u * 64u, ucol + 32, m0);
+        tma_store_commit();
+        tma_store_wait_read();                            // staging boxes may be rewritten
+        PL_PROBE(12 + crank, t);
+      }
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      if (et == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this CTA's h_t slice is in global memory
+        PL_PROBE(14 + crank, t);
+        red_release_gpu_add(flag, 1u);
+        PL_PROBE(16 + crank, t);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();      // neither CTA leaves while the peer may still signal its barriers / read its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 256);
+  }
+}
+
 // box_cols x box_rows map with an explicit swizzle (the h store uses 32-column = 64-byte rows)
 inline int get_map_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                       uint32_t box_cols, CUtensorMapSwizzle sw) {
@@ -309,8 +523,8 @@ inline int get_map_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return VC_OK;
 }
 
-inline size_t plstm_smem_bytes(int H) {
-  return (size_t)(H / BK) * kBoxBytes + (size_t)kPlStages * kBoxBytes + 2 * (128 * 64) + 1024;
+inline size_t plstm_smem_bytes(int H, int stages = kPlStages) {
+  return (size_t)(H / BK) * kBoxBytes + (size_t)stages * kBoxBytes + 2 * (128 * 64) + 1024;
 }
 
 // Largest batch one cooperative launch can take (0 = shape not supported by the persistent kernel).
@@ -324,7 +538,7 @@ inline int plstm_max_batch(int H, int num_sms) {
 // One bidirectional layer, all T steps.  out: [B, T, 2H] bf16 (written), xp: [B, T, 8H] bf16 (both directions'
 // input projections incl. biases, gate-interleaved), W[dir]: [4H, H] bf16 gate-interleaved, flags: >= 4*MT uints.
 inline int launch_lstm_layer_persistent(bf16* out, const bf16* xp, const void* W0, const void* W1, int B, int T, int H,
-                                        unsigned int* flags, cudaStream_t stream, long long* dbg = nullptr) {
+                                        unsigned int* flags, cudaStream_t stream, long long* dbg = nullptr, int pair_mode = -1) {
   PLstmMaps mp;
   VC_TRY(get_map(&mp.out_ld, out, (uint64_t)B, (uint64_t)T * 2 * H, (uint64_t)T * 2 * H, BM, 2));
   VC_TRY(get_map_sw(&mp.out_st, out, (uint64_t)B, (uint64_t)T * 2 * H, (uint64_t)T * 2 * H, 128, 32, CU_TENSOR_MAP_SWIZZLE_64B));
@@ -340,6 +554,22 @@ inline int launch_lstm_layer_persistent(bf16* out, const bf16* xp, const void* W
   dim3 grid(NT, MT, 2);
   VC_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * (size_t)4 * MT, stream));
   const size_t smem = plstm_smem_bytes(H);
+  // VC_PLSTM_PAIR=1: the CTA-pair form (measured slower: 8.7 vs 7.2 us per step, see its header); read per call like the other switches
+  const char* e = getenv("VC_PLSTM_PAIR");
+  const bool pair = (pair_mode < 0 ? (e != nullptr && e[0] == '1') : pair_mode != 0) && NT % 2 == 0;
+  if (pair) {
+    const size_t smem = plstm_smem_bytes(H, kPlPairStages);
+    VC_CUDA(cudaFuncSetAttribute(lstm_layer_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(kPlThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;            // all CTAs co-resident: the flag spins cannot starve a CTA that has not started
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    VC_CUDA(cudaLaunchKernelEx(&cfg, lstm_layer_pair_kernel, mp, a));
+    return VC_OK;
+  }
   VC_CUDA(cudaFuncSetAttribute(lstm_layer_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&mp, (void*)&a};
   VC_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_layer_persistent_kernel, grid, dim3(kPlThreads), args, smem, stream));
