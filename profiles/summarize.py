@@ -73,5 +73,45 @@ def raw(src, dst):
             f.write("| top stall reasons (samples) | " + ", ".join(f"{h} {int(v)}" for h, v in top) + " | |\n")
 
 
+# kernel name fragment -> bench.py kernel class (VC_CLS_*), benchmark workload
+CLASS_OF = [
+    ("gemm_tc_persistent_kernel<4, 0, __nv_bfloat16, 0, 0, 1, 1, 0>", "enc_feature_proj"),
+    ("lstm_layer_persistent_kernel", "enc_recurrent"), ("lstm_layer_pair_kernel", "enc_recurrent"),
+    ("gemm_tc_kernel<128, 3, 2, 0, __half", "attn_query_proj"),
+    ("attn_additive_ws_kernel", "attn_step"),
+    ("gemm_tc_persistent_kernel<5, 1,", "dec_lstm"),
+    ("gemm_tc_kernel<128, 3, 2, 0, __nv_bfloat16, 1", "dec_context_proj"),
+    ("gemm_tc_persistent_kernel<3, 0, float, 0, 1", "dec_vocab"),
+    ("select_fused_kernel", "select"),
+    ("reorder_embed_kernel", "reorder_embed"),
+]
+
+
+def traffic(src, dst):
+    """Per-launch DRAM bytes of the kernel classes from a --set full capture -> the JSON bench.py reads (roofline.traffic)."""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+    acc = collections.OrderedDict()
+    for r in rows[2:]:
+        name = short(r[idx["Kernel Name"]])
+        cls = next((c for frag, c in CLASS_OF if frag in name), None)
+        if cls is None:
+            continue
+        b = sum(float(r[idx[m]].replace(",", "")) * scale[units[idx[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        t = float(r[idx["gpu__time_duration.sum"]].replace(",", "")) * tscale[units[idx["gpu__time_duration.sum"]]]
+        a = acc.setdefault(cls, [0.0, 0.0, 0])
+        a[0] += b; a[1] += t; a[2] += 1
+    d = {"source": f"{src} (ncu --set full --clock-control none, scripts/profile_round.sh): dram__bytes_read.sum + dram__bytes_write.sum "
+                   "per launch, workload c2_beam5_msvd_bf16 B=1024",
+         "classes": {c: {"dram_bytes_per_launch": a[0] / a[2], "ncu_duration_us": a[1] / a[2], "launches_captured": a[2]}
+                     for c, a in acc.items()}}
+    json.dump(d, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "raw": raw, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -464,7 +464,7 @@ def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
     def run(**env):
         for k in ("VC_DISABLE_LAYER_SYNC", "VC_DISABLE_CTX_HANDOVER", "VC_DISABLE_MC", "VC_DISABLE_PDL", "VC_DISABLE_SHARED_THR",
                   "VC_CUDA_GRAPHS", "VC_DISABLE_EARLY_Q", "VC_DISABLE_VOCAB_HANDOVER", "VC_DISABLE_ATTN_GATHER", "VC_CTX_PERSISTENT",
-                  "VC_PLSTM_PAIR"):
+                  "VC_PLSTM_PAIR", "VC_DISABLE_LSTM_MERGE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -490,7 +490,9 @@ def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
                 dict(VC_DISABLE_VOCAB_HANDOVER="1"), dict(VC_DISABLE_VOCAB_HANDOVER="1", VC_DISABLE_CTX_HANDOVER="1"),
                 dict(VC_DISABLE_ATTN_GATHER="1"),       # reorder / embedding gather as its own launch vs inside the attention kernel
                 dict(VC_CTX_PERSISTENT="1"), dict(VC_CTX_PERSISTENT="2"),      # context projection on the persistent kernels
-                dict(VC_PLSTM_PAIR="1")):               # encoder recurrence on CTA pairs
+                dict(VC_PLSTM_PAIR="1"),                # encoder recurrence on CTA pairs
+                dict(VC_DISABLE_LSTM_MERGE="1"),        # the decoder's two LSTM layers as two launches instead of one
+                dict(VC_DISABLE_LSTM_MERGE="1", VC_DISABLE_LAYER_SYNC="1"), dict(VC_DISABLE_MC="1")):
         got = run(**env)
         for k in ref:
             assert torch.equal(got[k], ref[k]), (env, k)
@@ -509,16 +511,19 @@ def test_ragged_full_size_batches(monkeypatch, B):
     g = torch.Generator(device="cuda").manual_seed(B)
     x = torch.randn(B, 80, 4096, generator=g, device="cuda")
     outs = []
-    for env in ({}, dict(VC_DISABLE_LAYER_SYNC="1", VC_DISABLE_MC="1", VC_DISABLE_PDL="1", VC_DISABLE_EARLY_Q="1", VC_CUDA_GRAPHS="0")):
-        for k in ("VC_DISABLE_LAYER_SYNC", "VC_DISABLE_MC", "VC_DISABLE_PDL", "VC_DISABLE_EARLY_Q", "VC_CUDA_GRAPHS"):
+    for env in ({}, dict(VC_DISABLE_LAYER_SYNC="1", VC_DISABLE_MC="1", VC_DISABLE_PDL="1", VC_DISABLE_EARLY_Q="1", VC_CUDA_GRAPHS="0"),
+                dict(VC_DISABLE_LSTM_MERGE="1", VC_DISABLE_ATTN_GATHER="1")):
+        for k in ("VC_DISABLE_LAYER_SYNC", "VC_DISABLE_MC", "VC_DISABLE_PDL", "VC_DISABLE_EARLY_Q", "VC_CUDA_GRAPHS", "VC_DISABLE_LSTM_MERGE",
+                  "VC_DISABLE_ATTN_GATHER"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         m = make_native_model(cfg, V, sd, "bahdanau", "bf16")
         o = m.generate(x, START, END, max_length=6, method="beam", beam_size=5)
         outs.append({k: v.cpu() for k, v in o.items()})
-    for k in outs[0]:
-        assert torch.equal(outs[0][k], outs[1][k]), k
+    for o in outs[1:]:
+        for k in outs[0]:
+            assert torch.equal(outs[0][k], o[k]), k
     tail = make_native_model(cfg, V, sd, "bahdanau", "bf16").generate(x[B - 40:].clone(), START, END, max_length=6, method="beam",
                                                                      beam_size=5)["generated_tokens"].cpu()
     L = tail.shape[1]

@@ -128,6 +128,7 @@ struct vc_model {
   bool feat_cvt = false;                  // VC_FEAT_CVT=1: feature projection with fp32 -> bf16 converting producer warps instead of tf32 operands
   bool early_attn = false;                // VC_EARLY_ATTN=1: the next step's attention also runs on the second stream, before the reorder
   int ctx_persistent = 0;                 // VC_CTX_PERSISTENT=1|2: context projection on the persistent 128x256-tile kernel / its CTA-pair form (A/B testing)
+  bool disable_lstm_merge = false;        // VC_DISABLE_LSTM_MERGE=1: the decoder's stacked LSTM layers as one launch each (A/B testing)
   bool disable_attn_gather = false;       // VC_DISABLE_ATTN_GATHER=1: reorder / embedding gather as a launch of its own instead of a warp of the attention kernel (A/B testing)
   bool disable_early_q = false;           // VC_DISABLE_EARLY_Q=1: query projection in place, after the reorder (A/B testing)
   cudaStream_t aux_stream = nullptr;      // second stream of the decode loop (early query projection)
@@ -903,12 +904,11 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
       gather_pending = false;
     }
     // L-layer LSTM, one step (:152): gates = [x | h_prev] . [W_ih | W_hh]^T + (b_ih + b_hh), fused cell
-    for (int l = 0; l < L; ++l) {
+    auto lstm_layer_args = [&](int l, GemmArgs& g, EpiLstm<ActT, ActT, P>& e, int64_t& lda) {
       const int in = (l == 0) ? (E + H) : H;
       const ActT* A = (l == 0) ? w.Z : w.XL[l];
-      const int64_t lda = (l == 0) ? ZW : 2 * H;
-      GemmArgs g = gargs(A, lda, m->dec_W[l], in + H, R, 4 * H, in + H);
-      EpiLstm<ActT, ActT, P> e;
+      lda = (l == 0) ? ZW : 2 * H;
+      g = gargs(A, lda, m->dec_W[l], in + H, R, 4 * H, in + H);
       memset(&e, 0, sizeof(e));
       e.bias[0] = e.bias[1] = m->dec_bias[l];
       e.c_prev[0] = e.c_prev[1] = w.C[l];
@@ -930,6 +930,26 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
         e.sync_wait = (l > 0) ? w.dec_sync + (size_t)(l - 1) * sync_rows : nullptr;
         e.sync_target = sync_arr * (unsigned int)(step + 1);
       }
+    };
+    bool lstm_done = false;
+    if constexpr (!P) {
+      // two stacked layers: one launch over both layers' tiles (gemm_tc.cuh: TcArgs::dual) instead of two kernels that hand
+      // tile rows over -- the same counters, but one balanced tile list, one prologue and one drain
+      if (L == 2 && sync_arr != 0 && !m->disable_lstm_merge) {
+        GemmArgs g0, g1;
+        EpiLstm<ActT, ActT, P> e0, e1;
+        int64_t lda0 = 0, lda1 = 0;
+        lstm_layer_args(0, g0, e0, lda0);
+        lstm_layer_args(1, g1, e1, lda1);
+        VC_SCOPE(VC_CLS_DEC_LSTM);
+        VC_TRY(tc::launch_gemm_tc_lstm_dual(g0, lda0, e0, g1, lda1, e1, s, &lstm_done));
+      }
+    }
+    for (int l = 0; l < L && !lstm_done; ++l) {
+      GemmArgs g;
+      EpiLstm<ActT, ActT, P> e;
+      int64_t lda = 0;
+      lstm_layer_args(l, g, e, lda);
       VC_SCOPE(VC_CLS_DEC_LSTM);
       VC_TRY((gemm<ActT>(g, lda, e, s)));
     }
@@ -1176,6 +1196,8 @@ int vc_model_create(const vc_model_desc_t* desc, vc_model_t** out) {
   m->disable_early_q = env != nullptr && env[0] == '1';
   env = getenv("VC_CTX_PERSISTENT");
   m->ctx_persistent = env != nullptr ? atoi(env) : 0;
+  env = getenv("VC_DISABLE_LSTM_MERGE");
+  m->disable_lstm_merge = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_ATTN_GATHER");
   m->disable_attn_gather = env != nullptr && env[0] == '1';
   env = getenv("VC_DISABLE_CTX_HANDOVER");

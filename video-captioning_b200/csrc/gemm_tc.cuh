@@ -247,6 +247,7 @@ struct alignas(64) TcMaps {
   // EPI_STORE: io[0] = C.  EPI_LSTM: io[0] = addend (input projections), io[1] = c_prev, io[2] = c_new,
   // io[3] = h destination 0, io[4] = h destination 1.
   CUtensorMap io[5];
+  CUtensorMap io1[5];     // dual-problem LSTM launch (TcArgs::dual): the io maps of problem z = 1
 };
 struct TcArgs {
   int M, N, K;
@@ -264,6 +265,16 @@ struct TcArgs {
   const unsigned int* sync_wait;
   unsigned int sync_target;
   int sync_row_shift;     // gemm_tc_kernel: counter index = m0 >> sync_row_shift
+  // Dual-problem form of the persistent EPI_LSTM kernel (the decoder's two stacked LSTM layers of one step in ONE launch, z =
+  // layer): the layers share M and N but not K, buffers or hand-over counters.  Tiles are ordered layer 0 first, so every CTA
+  // (pair) finishes its layer-0 tiles before it waits on a layer-1 tile's rows (sync_wait1: the same per-tile-row counters
+  // layer 0 signals), and the ring streams across the layer boundary: the partial last tile round of layer 0 and the launch /
+  // prologue / drain of a second kernel disappear into one balanced tile list.  z = 0 uses K, io[], sync_signal (and the
+  // grid-level dependency wait); z = 1 uses K1, io1[], sync_wait1 / sync_signal1.
+  int dual;
+  int K1;
+  unsigned int* sync_signal1;
+  const unsigned int* sync_wait1;
   const float* a32;       // CVT kernels: the fp32 A operand [M, lda32] (converted to bf16 by the producer warps)
   int64_t lda32;
 #ifdef VC_GEMM_PROBE
@@ -657,6 +668,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
   const int tiles_z = (tiles_m / kMT) * tiles_n;                                     // tiles of one z (direction)
   const int num_tiles = tiles_z * ((EPI == EPI_LSTM && g.nz > 1) ? g.nz : 1);
   const bool has_add = EPI == EPI_LSTM && g.has_add != 0;
+  const bool dual = EPI == EPI_LSTM && g.dual != 0;                                  // two stacked layers in one launch (TcArgs::dual)
+  auto nkb_of = [&](int z) { return (dual && z != 0) ? g.K1 / BKE : nkb; };
   uint8_t* ident_s = nullptr;                                                        // identity block of the addend MMAs
   // tile schedule (m-major tile index, n fastest): round-robin, or contiguous ranges when the epilogue carries
   // per-row state from tile to tile (STATS)
@@ -748,10 +761,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
       for (int tile = t_first; tile < t_last; tile += t_step, ++it) {
         const int z = tile_z(tile), tz = tile - z * tiles_z;
         const int m0 = ((tz / tiles_n) * kMT + crank) * BM, n0 = (tz % tiles_n) * BN;
-        if (g.sync_wait != nullptr) {
+        const unsigned int* sync_wait = (dual && z != 0) ? g.sync_wait1 : g.sync_wait;
+        if (sync_wait != nullptr) {
           // the producer GEMM (still running: the previous LSTM layer, or the context projection in front of the vocabulary
-          // projection) publishes its rows per m-tile row: acquire them
-          const unsigned int* flag = g.sync_wait + tz / tiles_n;
+          // projection; dual form: layer 0's tiles of this launch) publishes its rows per m-tile row: acquire them
+          const unsigned int* flag = sync_wait + tz / tiles_n;
           uint32_t spin = 0;
           while (ld_acquire_gpu_u32(flag) < g.sync_target) {
             if (++spin > (1u << 26)) {
@@ -762,7 +776,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           asm volatile("fence.proxy.async;" ::: "memory");   // order the acquire before the async-proxy loads
         }
         GEMM_PROBE(it, 0);
-        for (int kb = 0; kb < nkb; ++kb) {
+        const CUtensorMap* io = (dual && z != 0) ? maps.io1 : maps.io;
+        const int nk = nkb_of(z);
+        for (int kb = 0; kb < nk; ++kb) {
           const bool pre = (it == 0 && kb < npre);         // W already on its way, barrier already armed
           const uint32_t fb = smem_u32(&full_bar[stage]);
           if (!pre) {
@@ -792,8 +808,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
           mbar_wait(smem_u32(&c_empty), (uint32_t)((it & 1) ^ 1));
           const uint32_t cb = smem_u32(&c_full);
           mbar_expect_tx(cb, 2 * kBoxBytes);
-          tma_load_2d(smem_u32(io_smem), &maps.io[1], cb, g.io_col0[1][z] + n0 / 4, m0);
-          tma_load_2d(smem_u32(io_smem + kBoxBytes), &maps.io[1], cb, g.io_col0[1][z] + n0 / 4 + 32, m0);
+          tma_load_2d(smem_u32(io_smem), &io[1], cb, g.io_col0[1][z] + n0 / 4, m0);
+          tma_load_2d(smem_u32(io_smem + kBoxBytes), &io[1], cb, g.io_col0[1][z] + n0 / 4 + 32, m0);
         }
       }
     }
@@ -809,7 +825,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         tc_fence_after();
         GEMM_PROBE(it, 1);
         const uint32_t d = tmem_base + (uint32_t)(a * BN);
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int nk = nkb_of(tile_z(tile));
+        for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           if (kb == 0) GEMM_PROBE(it, 2);
           tc_fence_after();
@@ -1173,20 +1190,22 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
         epi_bar_sync();
         if (et == 0) {
           const int u_tile = n0 / 4;
-          tma_store_2d(&maps.io[3], h_box, g.io_col0[3][z] + u_tile, m0);
-          if (g.has_h1) tma_store_2d(&maps.io[4], h_box, g.io_col0[4][z] + u_tile, m0);
-          tma_store_2d(&maps.io[2], c_s, g.io_col0[2][z] + u_tile, m0);
-          tma_store_2d(&maps.io[2], c_s + kBoxBytes, g.io_col0[2][z] + u_tile + 32, m0);
+          const CUtensorMap* io = (dual && z != 0) ? maps.io1 : maps.io;
+          tma_store_2d(&io[3], h_box, g.io_col0[3][z] + u_tile, m0);
+          if (g.has_h1) tma_store_2d(&io[4], h_box, g.io_col0[4][z] + u_tile, m0);
+          tma_store_2d(&io[2], c_s, g.io_col0[2][z] + u_tile, m0);
+          tma_store_2d(&io[2], c_s + kBoxBytes, g.io_col0[2][z] + u_tile + 32, m0);
           tma_store_commit();
           tma_store_wait_read();
           GEMM_PROBE(it, 6);
           mbar_arrive_cta(smem_u32(&c_empty));          // c / h boxes may be refilled for the next tile
-          if (g.sync_signal != nullptr) {
+          unsigned int* sync_signal = (dual && z != 0) ? g.sync_signal1 : g.sync_signal;
+          if (sync_signal != nullptr) {
             // publish this tile's h rows to the next layer's GEMM: stores complete, then a release increment
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async;" ::: "memory");
             __threadfence();
-            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(g.sync_signal + tz / tiles_n), "r"(1u) : "memory");
+            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(sync_signal + tz / tiles_n), "r"(1u) : "memory");
           }
         }
         epi_bar_sync();                                 // nobody rewrites h_box before the stores have read it
@@ -1703,6 +1722,80 @@ inline int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiLstm<bf16,
     VC_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, mp, ta));
   }
   VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ---- the decoder's two stacked LSTM layers of one step in ONE launch (TcArgs::dual).  g0 / e0: layer 0, g1 / e1: layer 1
+// (decoder form: one problem each, no addend, staged cell-state tiles); e0.sync_signal -> the per-tile-row counters layer 1
+// waits on (e1.sync_wait), e1.sync_signal -> the next consumer's (the context projection).  Returns VC_ERR_UNSUPPORTED-like
+// false through `*taken` when the shapes do not take the persistent kernel, so the caller launches the layers one by one.
+inline int launch_gemm_tc_lstm_dual(const GemmArgs& g0, int64_t a_cols0, const EpiLstm<bf16, bf16, false>& e0, const GemmArgs& g1,
+                                    int64_t a_cols1, const EpiLstm<bf16, bf16, false>& e1, cudaStream_t stream, bool* taken) {
+  *taken = false;
+  const int H = g0.N / 4;
+  const bool ok = g0.M == g1.M && g0.N == g1.N && g0.M > 0 && g0.N % 256 == 0 && g0.nz == 1 && g1.nz == 1 && e0.lengths == nullptr &&
+                  e1.lengths == nullptr && e0.c_tma_cols > 0 && e1.c_tma_cols > 0 && e0.addend[0] == nullptr && e1.addend[0] == nullptr &&
+                  e0.sync_signal != nullptr && e1.sync_wait == e0.sync_signal && e0.sync_wait == nullptr &&
+                  (e0.h_out1[0] != nullptr) == (e1.h_out1[0] != nullptr);
+  const int tm = (g0.M + BM - 1) / BM, tn = g0.N / 256;
+  if (!ok || tm * tn < num_sms()) return VC_OK;
+  TcMaps mp, mq;
+  TcArgs ta, tb;
+  const GemmArgs* gs[2] = {&g0, &g1};
+  const EpiLstm<bf16, bf16, false>* es[2] = {&e0, &e1};
+  const int64_t acs[2] = {a_cols0, a_cols1};
+  const bool mc = use_mc(tm, tn);      // (the same decision lstm_sync_arrivals() bases the counters' targets on)
+  for (int l = 0; l < 2; ++l) {
+    TcMaps& m_ = l == 0 ? mp : mq;
+    TcArgs& t_ = l == 0 ? ta : tb;
+    const GemmArgs& g = *gs[l];
+    const EpiLstm<bf16, bf16, false>& e = *es[l];
+    VC_CHECK(g.a_split >= g.K, "dual LSTM launch: split A operands are not supported");
+    VC_TRY(fill_ab(m_, t_, g, acs[l], 256));
+    if (mc) VC_TRY(fill_w_half(m_, g, 2));
+    t_.bias[0] = e.bias[0];
+    Ref rc{e.c_prev[0], e.c_origin_in, e.c_tma_cols, e.c_ld};
+    VC_TRY(ref_map(&m_.io[1], &t_.io_col0[1][0], rc, (uint64_t)g.M, BM, 4));
+    Ref rn{e.c_new[0], e.c_origin_out, e.c_tma_cols, e.c_ld};
+    VC_TRY(ref_map(&m_.io[2], &t_.io_col0[2][0], rn, (uint64_t)g.M, BM, 4));
+    Ref rh{e.h_out0[0], e.h0_origin, e.h0_origin ? e.h0_origin_cols : (int64_t)H, e.h0_ld};
+    VC_TRY(ref_map(&m_.io[3], &t_.io_col0[3][0], rh, (uint64_t)g.M, BM, 2));
+    if (e.h_out1[0] != nullptr) {
+      Ref r1{e.h_out1[0], e.h1_origin, e.h1_origin ? e.h1_origin_cols : (int64_t)H, e.h1_ld};
+      VC_TRY(ref_map(&m_.io[4], &t_.io_col0[4][0], r1, (uint64_t)g.M, BM, 2));
+      t_.has_h1 = 1;
+    }
+  }
+  // problem 1 -> the z = 1 slots of problem 0's launch arguments
+  mp.A[1] = mq.A[0]; mp.W[1] = mq.W[0]; mp.Wh[1] = mq.Wh[0];
+  for (int i = 0; i < 5; ++i) { mp.io1[i] = mq.io[i]; ta.io_col0[i][1] = tb.io_col0[i][0]; }
+  mp.io1[0] = mp.io[0] = mp.io[1];     // (addend maps are never used in the decoder form; keep them valid)
+  ta.a_col0[1] = tb.a_col0[0];
+  ta.bias[1] = tb.bias[0];
+  ta.dual = 1; ta.K1 = g1.K; ta.nz = 2; ta.has_add = 0;
+  ta.sync_wait = nullptr; ta.sync_signal = e0.sync_signal;
+  ta.sync_wait1 = e1.sync_wait; ta.sync_signal1 = e1.sync_signal;
+  ta.sync_target = e1.sync_target;
+  VocabStats vs;
+  memset(&vs, 0, sizeof(vs));
+#ifdef VC_GEMM_PROBE
+  ta.dbg = probe_dbg();
+#endif
+  if (mc) {
+    constexpr int kMcStages = 5;
+    const size_t smem_mc = (size_t)kMcStages * (BM * BK * 2 + 128 * BK * 2) + 3 * kBoxBytes + 1024;
+    auto kern = gemm_tc_persistent_kernel<kMcStages, EPI_LSTM, bf16, false, false, false, true>;
+    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mc));
+    VC_CUDA(launch_pdl_cluster(kern, dim3(num_sms()), dim3(PersistentCfg<EPI_LSTM>::kThreads), smem_mc, stream, 2, mp, ta, tm, tn, vs));
+  } else {
+    constexpr int kStages = 3;
+    const size_t smem = (size_t)kStages * (BM * BK * 2 + 256 * BK * 2) + 3 * kBoxBytes + 1024;
+    auto kern = gemm_tc_persistent_kernel<kStages, EPI_LSTM, bf16, false, false>;
+    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VC_CUDA(launch_pdl(kern, dim3(num_sms()), dim3(PersistentCfg<EPI_LSTM>::kThreads), smem, stream, mp, ta, tm, tn, vs));
+  }
+  VC_CUDA(cudaGetLastError());
+  *taken = true;
   return VC_OK;
 }
 
