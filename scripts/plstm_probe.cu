@@ -60,15 +60,17 @@ int main(int argc, char** argv) {
   const int reps = 10;
   float ms = 0.f;
   const int pair_last = getenv("PROBE_PAIR") ? atoi(getenv("PROBE_PAIR")) : 1;
-  for (int mode = 0; mode < 2; ++mode) {
-    const int pair = mode == 0 ? 1 - pair_last : pair_last;      // both forms on the same operands: the checksums must agree
+  const int cluster = getenv("PROBE_CLUSTER") ? atoi(getenv("PROBE_CLUSTER")) : 1;
+  for (int mode = 0; mode < 3; ++mode) {
+    // single CTA, single CTA in clusters of two (multicast h boxes), CTA pairs: the checksums must agree
+    const int pair = mode == 2 ? 1 : 0, cl = mode == 1 ? 2 : 1;
     CK(cudaMemset(out, 0, (size_t)B * T * 2 * H * 2));
     for (int i = 0; i < 3; ++i)
-      if (vc::tc::launch_lstm_layer_persistent(out, xp, W0, W1, B, T, H, flags, 0, nullptr, pair) != 0) return 2;
+      if (vc::tc::launch_lstm_layer_persistent(out, xp, W0, W1, B, T, H, flags, 0, nullptr, pair, cl) != 0) return 2;
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
     for (int i = 0; i < reps; ++i)
-      if (vc::tc::launch_lstm_layer_persistent(out, xp, W0, W1, B, T, H, flags, 0, nullptr, pair) != 0) return 2;
+      if (vc::tc::launch_lstm_layer_persistent(out, xp, W0, W1, B, T, H, flags, 0, nullptr, pair, cl) != 0) return 2;
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms, e0, e1);
@@ -76,10 +78,10 @@ int main(int argc, char** argv) {
     checksum_kernel<<<512, 256>>>(out, (size_t)B * T * 2 * H, cs);
     unsigned long long hcs = 0;
     CK(cudaMemcpy(&hcs, cs, 8, cudaMemcpyDeviceToHost));
-    printf("%s B=%d T=%d H=%d: %.3f ms per layer (%.2f us per step), checksum %llx\n", pair ? "pair  " : "single", B, T, H, ms / reps,
+    printf("%s B=%d T=%d H=%d: %.3f ms per layer (%.2f us per step), checksum %llx\n", pair ? "pair    " : (cl == 2 ? "cluster2" : "single  "), B, T, H, ms / reps,
            ms / reps * 1000.f / T, hcs);
   }
-  if (vc::tc::launch_lstm_layer_persistent(out, xp, W0, W1, B, T, H, flags, 0, dbg, pair_last) != 0) return 2;
+  if (vc::tc::launch_lstm_layer_persistent(out, xp, W0, W1, B, T, H, flags, 0, dbg, pair_last == 1 && cluster == 1 ? 1 : 0, cluster) != 0) return 2;
   CK(cudaDeviceSynchronize());
   long long h[8 * 32];
   CK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));

@@ -464,7 +464,7 @@ def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
     def run(**env):
         for k in ("VC_DISABLE_LAYER_SYNC", "VC_DISABLE_CTX_HANDOVER", "VC_DISABLE_MC", "VC_DISABLE_PDL", "VC_DISABLE_SHARED_THR",
                   "VC_CUDA_GRAPHS", "VC_DISABLE_EARLY_Q", "VC_DISABLE_VOCAB_HANDOVER", "VC_DISABLE_ATTN_GATHER", "VC_CTX_PERSISTENT",
-                  "VC_PLSTM_PAIR", "VC_DISABLE_LSTM_MERGE"):
+                  "VC_PLSTM_PAIR", "VC_PLSTM_CLUSTER", "VC_DISABLE_LSTM_MERGE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -491,6 +491,7 @@ def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
                 dict(VC_DISABLE_ATTN_GATHER="1"),       # reorder / embedding gather as its own launch vs inside the attention kernel
                 dict(VC_CTX_PERSISTENT="1"), dict(VC_CTX_PERSISTENT="2"),      # context projection on the persistent kernels
                 dict(VC_PLSTM_PAIR="1"),                # encoder recurrence on CTA pairs
+                dict(VC_PLSTM_CLUSTER="2"),             # ... in clusters of two with multicast h boxes
                 dict(VC_DISABLE_LSTM_MERGE="1"),        # the decoder's two LSTM layers as two launches instead of one
                 dict(VC_DISABLE_LSTM_MERGE="1", VC_DISABLE_LAYER_SYNC="1"), dict(VC_DISABLE_MC="1")):
         got = run(**env)

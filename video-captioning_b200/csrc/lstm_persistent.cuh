@@ -84,6 +84,25 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned in
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// TMA load delivered to the same shared-memory offset of every CTA in `mask` of the cluster; each destination's barrier (same
+// offset) receives the bytes
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// completion of this CTA's MMAs -> the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+
+// CL = 1: one CTA per (gate-column tile, row tile, direction) as described above.  CL = 2 (clusters of two neighbouring
+// gate-column tiles, which need the same h_{t-1} rows): the two producers issue alternate k-blocks and TMA-multicast each box
+// into both CTAs' rings, so a box leaves L2 once per cluster instead of twice; a ring slot is refilled when BOTH CTAs' MMAs
+// have consumed it (tcgen05.commit multicast onto both empty barriers).  MMAs, epilogue and flags are unchanged.
+template <int CL>
 __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(const __grid_constant__ PLstmMaps maps,
                                                                              const PLstmArgs g) {
   extern __shared__ uint8_t smem_raw[];
@@ -103,13 +122,14 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
   const int n0 = blockIdx.x * kPlBN;                      // gate column tile
   const int m0 = blockIdx.y * 256;                        // row tile
   const int NT = gridDim.x;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
   unsigned int* flag0 = g.flags + ((size_t)(z * gridDim.y + blockIdx.y) * 2);
 
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&w_bar), 1);
     for (int s = 0; s < kPlStages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), CL);               // one commit per CTA of the cluster
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(smem_u32(&tmem_full[h]), 1);
@@ -123,7 +143,8 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 256);
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();                           // the peer's barriers are initialised before anything lands on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -153,7 +174,9 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
             const uint32_t fb = smem_u32(&full_bar[stage]);
             mbar_expect_tx(fb, kBoxBytes);
-            tma_load_2d(smem_u32(a_s + (size_t)stage * kBoxBytes), &maps.out_ld, fb, col0 + kb * BK, m0 + half * 128);
+            if (CL == 1) tma_load_2d(smem_u32(a_s + (size_t)stage * kBoxBytes), &maps.out_ld, fb, col0 + kb * BK, m0 + half * 128);
+            else if ((kb & 1) == crank)
+              tma_load_2d_mcast(smem_u32(a_s + (size_t)stage * kBoxBytes), &maps.out_ld, fb, col0 + kb * BK, m0 + half * 128, (uint16_t)3);
             if (++stage == kPlStages) { stage = 0; phase ^= 1; }
           }
           PL_PROBE(2 + half, t);
@@ -180,7 +203,8 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
               umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_commit(smem_u32(&empty_bar[stage]));
+            if (CL == 1) umma_commit(smem_u32(&empty_bar[stage]));
+            else umma_commit_mcast(smem_u32(&empty_bar[stage]), (uint16_t)3);     // slot consumed by this CTA: tell both producers
             if (++stage == kPlStages) { stage = 0; phase ^= 1; }
           }
           umma_commit(smem_u32(&tmem_full[half]));
@@ -285,7 +309,8 @@ __global__ void __launch_bounds__(kPlThreads, 1) lstm_layer_persistent_kernel(co
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();                           // neither CTA leaves while the peer may still write its ring / barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
@@ -538,7 +563,7 @@ inline int plstm_max_batch(int H, int num_sms) {
 // One bidirectional layer, all T steps.  out: [B, T, 2H] bf16 (written), xp: [B, T, 8H] bf16 (both directions'
 // input projections incl. biases, gate-interleaved), W[dir]: [4H, H] bf16 gate-interleaved, flags: >= 4*MT uints.
 inline int launch_lstm_layer_persistent(bf16* out, const bf16* xp, const void* W0, const void* W1, int B, int T, int H,
-                                        unsigned int* flags, cudaStream_t stream, long long* dbg = nullptr, int pair_mode = -1) {
+                                        unsigned int* flags, cudaStream_t stream, long long* dbg = nullptr, int pair_mode = -1, int cluster_mode = -1) {
   PLstmMaps mp;
   VC_TRY(get_map(&mp.out_ld, out, (uint64_t)B, (uint64_t)T * 2 * H, (uint64_t)T * 2 * H, BM, 2));
   VC_TRY(get_map_sw(&mp.out_st, out, (uint64_t)B, (uint64_t)T * 2 * H, (uint64_t)T * 2 * H, 128, 32, CU_TENSOR_MAP_SWIZZLE_64B));
@@ -570,9 +595,26 @@ inline int launch_lstm_layer_persistent(bf16* out, const bf16* xp, const void* W
     VC_CUDA(cudaLaunchKernelEx(&cfg, lstm_layer_pair_kernel, mp, a));
     return VC_OK;
   }
-  VC_CUDA(cudaFuncSetAttribute(lstm_layer_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // VC_PLSTM_CLUSTER=2: clusters of two gate-column tiles share every h_{t-1} box through TMA multicast (A/B testing)
+  const char* ec = getenv("VC_PLSTM_CLUSTER");
+  const bool cl2 = (cluster_mode < 0 ? (ec != nullptr && ec[0] == '2') : cluster_mode == 2) && NT % 2 == 0;
+  if (cl2) {
+    VC_CUDA(cudaFuncSetAttribute(lstm_layer_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(kPlThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = 2; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    VC_CUDA(cudaLaunchKernelEx(&cfg, lstm_layer_persistent_kernel<2>, mp, a));
+    return VC_OK;
+  }
+  VC_CUDA(cudaFuncSetAttribute(lstm_layer_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&mp, (void*)&a};
-  VC_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_layer_persistent_kernel, grid, dim3(kPlThreads), args, smem, stream));
+  VC_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_layer_persistent_kernel<1>, grid, dim3(kPlThreads), args, smem, stream));
   return VC_OK;
 }
 
