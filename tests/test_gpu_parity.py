@@ -146,7 +146,7 @@ def test_masked_encoder_vs_oracle():
     assert torch.equal(out["generated_tokens"].cpu(), ref["generated_tokens"])
 
 
-@pytest.mark.parametrize("B,K,groups", [(3, 5, "41"), (5, 1, "31"), (7, 3, "42"), (300, 5, "41"), (310, 5, "51")])
+@pytest.mark.parametrize("B,K,groups", [(3, 5, "41"), (5, 1, "31"), (7, 3, "42"), (300, 5, "41"), (310, 5, "51"), (305, 5, "21"), (298, 3, "31")])
 def test_persistent_attention_kernel(monkeypatch, B, K, groups):
     """bf16 additive attention, persistent warp-specialised kernel (attention.cuh v5: unit-interleaved scoring groups,
     online softmax in the context groups): context and weights against the oracle (2e-2) and against the one-CTA-per-

@@ -1262,10 +1262,12 @@ inline int attn_num_sms() {
   }
   return n;
 }
-inline int attn_ws_groups() {          // VC_ATTN_GROUPS=NG*10+NCG: scoring / context groups per CTA (A/B testing); default 41
+inline int attn_ws_groups() {          // VC_ATTN_GROUPS=NG*10+NCG: scoring / context groups per CTA (A/B testing); default 31
+  // (three scoring groups since the CTA also carries the two row-gather warps: 1.63 vs 1.67 ms per 20 launches at C2; before
+  // that 41 and 31 measured the same)
   const char* e = getenv("VC_ATTN_GROUPS");
-  const int v = e != nullptr ? atoi(e) : 41;
-  return (v == 31 || v == 41 || v == 42 || v == 51 || v == 52) ? v : 41;
+  const int v = e != nullptr ? atoi(e) : 31;
+  return (v == 21 || v == 31 || v == 41 || v == 42 || v == 51 || v == 52) ? v : 31;
 }
 // The persistent kernel needs at least two videos per SM to beat v4 (one CTA per video); VC_ATTN_WS_MIN_B overrides the
 // threshold (tests run it on small batches)
@@ -1305,11 +1307,12 @@ inline int launch_attn_additive_ws(const AttnAddArgs& a, int K, cudaStream_t str
            a.B, K, a.D, a.H, a.T);
   VC_CHECK(a.ctx_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.ctx) & 15) == 0, "additive attention (ws): ctx must be 16-byte aligned");
   switch (attn_ws_groups()) {
-    case 31: return launch_attn_additive_ws_cfg<3, 1>(a, K, stream, rg);
+    case 21: return launch_attn_additive_ws_cfg<2, 1>(a, K, stream, rg);
+    case 41: return launch_attn_additive_ws_cfg<4, 1>(a, K, stream, rg);
     case 42: return launch_attn_additive_ws_cfg<4, 2>(a, K, stream, rg);
     case 51: return launch_attn_additive_ws_cfg<5, 1>(a, K, stream, rg);
     case 52: return launch_attn_additive_ws_cfg<5, 2>(a, K, stream, rg);
-    default: return launch_attn_additive_ws_cfg<4, 1>(a, K, stream, rg);
+    default: return launch_attn_additive_ws_cfg<3, 1>(a, K, stream, rg);
   }
 }
 
