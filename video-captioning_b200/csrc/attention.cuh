@@ -823,7 +823,10 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) attn_additive_mma_kernel(co
 // When the attention weights are requested the raw scores of a video stay in shared memory and are normalised with
 // the final (max, sum) at the end of the video.
 constexpr int kWsPartSlots = 8;
-constexpr int kWsEncSlots = 6;
+#ifndef VC_WS_ENC_SLOTS
+#define VC_WS_ENC_SLOTS 6
+#endif
+constexpr int kWsEncSlots = VC_WS_ENC_SLOTS;
 
 __device__ __forceinline__ void amb_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
