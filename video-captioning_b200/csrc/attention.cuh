@@ -419,6 +419,12 @@ __device__ __forceinline__ __half2 additive4_h2(const uint4& key, const uint4& q
   return acc;
 }
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// the same load as a volatile asm statement: it keeps its place among the other volatile asm statements (the MMAs)
+__device__ __forceinline__ uint4 ldg128_pinned(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
 // coherent 16-byte load: for data written by the previous kernel of the stream and read after pdl_wait()
 __device__ __forceinline__ uint4 ld128(const void* p) {
   uint4 r;
@@ -1050,19 +1056,25 @@ __global__ void __launch_bounds__(32 * (4 * NG + 4 * NCG + 1 + kGatherWarps), 1)
         const int fb = sw + 4 * j;
         if (fb >= nfb) break;
         uint4 nx0 = make_uint4(0u, 0u, 0u, 0u), nx1 = nx0;
-        if (fb + 4 < nfb) {
-          nx0 = ldg128(k0p + (fb + 4) * 32);
-          nx1 = ldg128(k1p + (fb + 4) * 32);
-        } else if (has_next) {
-          nx0 = ldg128(nbase + (int64_t)n0 * D);
-          nx1 = ldg128(nbase + (int64_t)n1 * D);
-        }
         const uint4 v4 = *reinterpret_cast<const uint4*>(v_s + fb * 32 + tg * 8);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           const uint4 q4 = *reinterpret_cast<const uint4*>(q + k * 128 + j * 32);
           mma_f16(acc[k], tanh_h2(key0.x, q4.x), tanh_h2(key1.x, q4.x), tanh_h2(key0.y, q4.y), tanh_h2(key1.y, q4.y), v4.x, v4.y);
           mma_f16(acc[k], tanh_h2(key0.z, q4.z), tanh_h2(key1.z, q4.z), tanh_h2(key0.w, q4.w), tanh_h2(key1.w, q4.w), v4.z, v4.w);
+          if (k == 0) {
+            // The next block's keys are requested only AFTER this block's key registers have been read for the first time
+            // (asm volatile loads between the first beam's MMAs and the second's).  Issued in front of the block, ptxas gave
+            // them the scoreboard of the loads this block is about to consume, so the first HADD2 of every other block waited
+            // for the loads just issued as well (16% of the scoring warps' stall samples, ncu source page of the r3 build).
+            if (fb + 4 < nfb) {
+              nx0 = ldg128_pinned(k0p + (fb + 4) * 32);
+              nx1 = ldg128_pinned(k1p + (fb + 4) * 32);
+            } else if (has_next) {
+              nx0 = ldg128_pinned(nbase + (int64_t)n0 * D);
+              nx1 = ldg128_pinned(nbase + (int64_t)n1 * D);
+            }
+          }
         }
         key0 = nx0;
         key1 = nx1;
