@@ -657,6 +657,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
   __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2], c_full, c_empty;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[2][BN];
+  __shared__ __align__(16) float stat_bias_s[STATS ? 8 * 2 * 128 : 4];      // STATS epilogue: a private bias copy per warp and accumulator
+  float* const stat_bias = stat_bias_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = g.K / BKE;
@@ -948,21 +950,35 @@ gemm_tc_persistent_kernel(const __grid_constant__ TcMaps maps, const TcArgs g, c
 #pragma unroll
           for (int j = 0; j < KS; ++j) top[j] = -INFINITY;
         }
-        float* bs = bias_s[a] + half * 128;
+        // the 128 bias values of this half: every warp stages its own copy (4 per lane) and only syncs with itself -- staged once
+        // per half behind a 128-thread barrier, the four warps of a half waited for each other at every tile (4% of the kernel's
+        // stall samples, ncu source page of the r3 build)
+        float* bs = stat_bias + (size_t)((warp - 2) * 2 + a) * 128;
         {
-          const int col = n0 + half * 128 + eh;
-          bs[eh] = (g.bias[0] != nullptr && col < g.N) ? g.bias[0][col] : 0.f;
+          const int col = n0 + half * 128 + lane * 4;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.bias[0] != nullptr) {
+            if (col + 3 < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias[0] + col));
+            else {
+              if (col < g.N) b4.x = g.bias[0][col];
+              if (col + 1 < g.N) b4.y = g.bias[0][col + 1];
+              if (col + 2 < g.N) b4.z = g.bias[0][col + 2];
+            }
+          }
+          *reinterpret_cast<float4*>(bs + lane * 4) = b4;
         }
         const int row = m0 + r;
         // threshold published by the other CTAs / the other column half working on this row (strictly-below test);
-        // read before the wait for the accumulator so that its latency is hidden
+        // requested before the wait for the accumulator and first looked at after it, so that its latency hides under that wait
         const bool shared_thr = vstat.rowthr != nullptr && vstat.topk > 0 && row < g.M;
-        const float gthr = shared_thr ? key2f(__ldcg(vstat.rowthr + row)) : -INFINITY;
+        int gkey = 0;
+        if (shared_thr) asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(gkey) : "l"(vstat.rowthr + row));
         const float thr_in = thr;
         mbar_wait(smem_u32(&tmem_full[a]), (uint32_t)((it >> 1) & 1));
         tc_fence_after();
         if (warp == 2 && lane == 0) GEMM_PROBE(it, 4);
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");          // bias of this half staged
+        __syncwarp();                                                         // this warp's bias copy is complete
+        const float gthr = shared_thr ? key2f(gkey) : -INFINITY;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + half * 128);
         const bool tail_tile = n0 + BN > g.N;
         // (the epilogue paces this kernel: ~4 us per tile against 2.3 us of main loop, scripts/gemm_probe.cu vocab; of the 25 us it
