@@ -490,6 +490,7 @@ def test_benchmark_path_variants_agree_at_full_size(monkeypatch):
                 dict(VC_DISABLE_VOCAB_HANDOVER="1"), dict(VC_DISABLE_VOCAB_HANDOVER="1", VC_DISABLE_CTX_HANDOVER="1"),
                 dict(VC_DISABLE_ATTN_GATHER="1"),       # reorder / embedding gather as its own launch vs inside the attention kernel
                 dict(VC_CTX_PERSISTENT="1"), dict(VC_CTX_PERSISTENT="2"),      # context projection on the persistent kernels
+                dict(VC_CTX_PERSISTENT="3"), dict(VC_CTX_PERSISTENT="0"),      # ... on 128 x 192 tiles / 128 x 128 tiles
                 dict(VC_PLSTM_PAIR="1"),                # encoder recurrence on CTA pairs
                 dict(VC_PLSTM_CLUSTER="2"),             # ... in clusters of two with multicast h boxes
                 dict(VC_DISABLE_LSTM_MERGE="1"),        # the decoder's two LSTM layers as two launches instead of one

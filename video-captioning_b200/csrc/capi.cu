@@ -127,7 +127,7 @@ struct vc_model {
   bool disable_fused_reorder = true;      // VC_FUSED_REORDER=1: the fused selection kernel also does the reorder/embedding gather (measured slower than the separate PDL launch: 54 vs 33 + 20 us per step)
   bool feat_cvt = false;                  // VC_FEAT_CVT=1: feature projection with fp32 -> bf16 converting producer warps instead of tf32 operands
   bool early_attn = false;                // VC_EARLY_ATTN=1: the next step's attention also runs on the second stream, before the reorder
-  int ctx_persistent = 0;                 // VC_CTX_PERSISTENT=1|2: context projection on the persistent 128x256-tile kernel / its CTA-pair form (A/B testing)
+  int ctx_persistent = 0;                 // VC_CTX_PERSISTENT=1|2: context projection on the persistent 128x256-tile kernel / its CTA-pair form (A/B testing); 3: 128x192 tiles, one CTA per SM
   bool disable_lstm_merge = false;        // VC_DISABLE_LSTM_MERGE=1: the decoder's stacked LSTM layers as one launch each (A/B testing)
   bool disable_attn_gather = false;       // VC_DISABLE_ATTN_GATHER=1: reorder / embedding gather as a launch of its own instead of a warp of the attention kernel (A/B testing)
   bool disable_early_q = false;           // VC_DISABLE_EARLY_Q=1: query projection in place, after the reorder (A/B testing)
@@ -985,13 +985,15 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
                            (mode == DM_BEAM || p.temperature == 1.0f);
     // context projection -> vocabulary projection hand-over: the 128x128-tile context kernel signals per 128-row tile, the
     // vocabulary GEMM (statistics form, single CTAs) starts on the tile rows that are complete while the rest is still running
-    const bool ctx_pers = !P && m->ctx_persistent != 0 && H >= 256;
+    const bool ctx_pers = !P && (m->ctx_persistent == 1 || m->ctx_persistent == 2) && H >= 256;
     const bool vocab_handover = !P && sync_arr != 0 && fused_sel && !m->disable_vocab_handover && tc::ctx_handover_ok(R, H) && H % 128 == 0 && !ctx_pers;
+    int ctx_tiles_n = H / 128;      // arrivals per 128-row tile on the context projection's hand-over counters
     {
       GemmArgs g = gargs(w.Z, ZW, m->Wc, 2 * H + E, R, H, 2 * H + E);
       g.a_split = E + H;
       g.a_skip = H;
-      g.force_persistent = ctx_pers ? m->ctx_persistent : 0;
+      g.force_persistent = ctx_pers ? m->ctx_persistent : (m->ctx_persistent == 3 ? 3 : 0);
+      if constexpr (!P) ctx_tiles_n = tc::store_tiles_n(g);
       if (sync_arr && !m->disable_ctx_handover && tc::ctx_handover_ok(R, H) && !ctx_pers) {
         // rows of h_top are taken over from the last LSTM layer's GEMM tile row by tile row (128x128-tile kernel only)
         g.sync_wait = w.dec_sync + (size_t)(L - 1) * sync_rows;
@@ -1022,7 +1024,7 @@ int run_decode(vc_model* m, WS<ActT>& w, int B, int T, int K, int S, const float
           GemmArgs gv = gargs(w.O, H, m->Wv, H, R, V, H);
           if (vocab_handover) {
             gv.sync_wait = w.dec_sync + (size_t)L * sync_rows;
-            gv.sync_target = (unsigned int)(H / 128) * (unsigned int)(step + 1);
+            gv.sync_target = (unsigned int)ctx_tiles_n * (unsigned int)(step + 1);
           }
           VC_TRY(gemm_vocab_stats(gv, H, estore<float, false, false>(lg, ldl, m->bv), s, vs));
         } else {

@@ -34,7 +34,8 @@ struct GemmArgs {
   // after its stores have completed.  nullptr: no signalling.
   unsigned int* sync_signal;
   // bf16 store GEMMs: 1 = take the persistent 128x256-tile kernel even with fewer tiles than SMs, 2 = its CTA-pair form
-  // (A/B testing of the context projection, VC_CTX_PERSISTENT); both ignore sync_wait / sync_signal
+  // (A/B testing of the context projection, VC_CTX_PERSISTENT); both ignore sync_wait / sync_signal.  3 = 128 x 192 tiles on the
+  // one-tile-per-CTA kernel when that makes a single wave at one CTA per SM (gemm_tc.cuh: wide_tiles_ok; keeps the hand-over)
   int force_persistent;
 };
 

@@ -327,7 +327,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs g) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(mapW) : "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), BN);
+  constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));   // allocations are powers of two
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -555,7 +556,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs g) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -1467,6 +1468,16 @@ inline bool ctx_handover_ok(int M, int N) {
   const int64_t tiles256 = (int64_t)((M + 127) / 128) * ((N + 255) / 256);
   return !(N >= 256 && tiles256 >= num_sms());
 }
+// 128 x 192 tiles for a small store GEMM (GemmArgs::force_persistent == 3): taken when they fit one CTA per SM in a single wave
+// where 128 x 128 tiles do not.  The 128 x 128 kernel at two CTAs per SM is bound by its ring's round trips (K / 64 k-blocks through
+// 3 slots, ~2 us each: 18.8 us for the context projection at 26% tensor-pipe activity with 160 CTAs = 0.54 waves); one CTA per SM
+// affords 5 slots.
+inline bool wide_tiles_ok(const GemmArgs& g) {
+  const int tm = (g.M + BM - 1) / BM;
+  return g.force_persistent == 3 && g.N > 256 && tm * ((g.N + 191) / 192) <= num_sms() && tm * ((g.N + 127) / 128) > num_sms();
+}
+// n-tiles (hand-over arrivals per 128-row tile) of the store GEMM [M, N] on the one-tile-per-CTA kernels
+inline int store_tiles_n(const GemmArgs& g) { return wide_tiles_ok(g) ? (g.N + 191) / 192 : (g.N + 127) / 128; }
 // maps.Wh[z] <- the W operand with a 128-row box (each CTA of a pair stages half of the 256-row tile)
 inline int fill_w_half(TcMaps& mp, const GemmArgs& g, int esize) {
   for (int z = 0; z < 2; ++z)
@@ -1521,8 +1532,8 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
   TcMaps mp;
   TcArgs ta;
   const int64_t tiles256 = (int64_t)((g.M + 127) / 128) * ((g.N + 255) / 256);
-  const int BN = (stats != nullptr || (g.N >= 256 && (tiles256 >= 148 || g.force_persistent != 0))) ? 256 : 128;
-  VC_TRY(fill_ab(mp, ta, g, a_cols, BN));
+  const int BN = (stats != nullptr || (g.N >= 256 && (tiles256 >= 148 || (g.force_persistent != 0 && g.force_persistent != 3)))) ? 256 : 128;
+  VC_TRY(fill_ab(mp, ta, g, a_cols, (BN == 128 && wide_tiles_ok(g)) ? 192 : BN));
   ta.bias[0] = ta.bias[1] = e.bias[0];
   VC_TRY(get_map(&mp.io[0], e.C[0], (uint64_t)g.M, (uint64_t)g.N, (uint64_t)e.ldc, BM, sizeof(OutT)));
   // consumer side of the tile-level hand-over (GemmArgs::sync_wait): the 128x128-tile kernel, and the single-CTA persistent
@@ -1582,6 +1593,14 @@ int launch_gemm_tc(const GemmArgs& g, int64_t a_cols, const EpiStore<OutT, TANH,
       VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       VC_CUDA(launch_pdl(kern, dim3(ctas), dim3(PersistentCfg<EPI_STORE>::kThreads), smem, stream, mp, ta, tm, tn, vs));
     }
+  } else if (wide_tiles_ok(g)) {
+    // 128 x 192 tiles, one CTA per SM, 5 stages x 40 KB (GemmArgs::force_persistent == 3: the context projection)
+    constexpr int kStages = 5;
+    const size_t smem = (size_t)kStages * (BM * BK * 2 + 192 * BK * 2) + 1024;
+    auto kern = gemm_tc_kernel<192, kStages, 1, EPI_STORE, OutT, TANH, false>;
+    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((g.N + 191) / 192, (g.M + BM - 1) / BM, 1);
+    VC_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, mp, ta));
   } else {
     // 3 stages x 32 KB: two CTAs co-reside per SM, so one CTA's epilogue overlaps the other's main loop
     constexpr int kStages = 3;
